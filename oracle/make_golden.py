@@ -1,0 +1,230 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE (oracle) -- generate tests/golden/*.npz by executing the reference's OWN,
+UNMODIFIED inference code from /root/reference on top of oracle/tf_shim (numpy stand-in for the TF
+ops; TensorFlow itself is not installable here).
+
+    python oracle/make_golden.py            # needs /root/reference; rewrites tests/golden/
+
+What runs unmodified:
+  * HM-16.5_Test_AI/bin/video_to_cu_depth.py (whole script, via runpy, argv = <yuv> W H QP, cwd holding
+    links to the deployed checkpoints + Thr_info.txt) -> the cu_depth.dat it writes is the golden
+    output.  Covers frame reading, zero padding, CTU slicing, <=1024 sub-batching, gates, writer.
+  * ETH-CNN_Training_LDP/net_CTU64.py net() with HM-16.5_Test_LDP/bin/model_LDP_2000000_qp22~37.dat
+    -> golden 21-vectors for residue CTUs (BASELINE config 5).
+  * HM-16.5_Test_LDP/bin/net_CNN_LSTM_one_step.py resi_cnn() -> golden 448-vectors (the FC1 tap).
+
+Each .npz stores the exact input bytes (or, for the one large case, the recipe + sha256) and the
+reference output, so the GPU box (which has no /root/reference) can check against them.
+"""
+from __future__ import annotations
+
+import hashlib
+import importlib
+import os
+import runpy
+import shutil
+import sys
+import tempfile
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+from oracle import ethcnn_oracle as eo  # noqa: E402
+
+REF = os.environ.get("ETHCNN_REFERENCE", "/root/reference")
+AI_BIN = os.path.join(REF, "HM-16.5_Test_AI", "bin")
+LDP_BIN = os.path.join(REF, "HM-16.5_Test_LDP", "bin")
+LDP_TRAIN = os.path.join(REF, "ETH-CNN_Training_LDP")
+SHIM = os.path.join(REPO, "oracle", "tf_shim")
+OUT = os.path.join(REPO, "tests", "golden")
+
+
+def _fresh_tf():
+    for m in [k for k in sys.modules if k == "tensorflow" or k.startswith("tensorflow.")]:
+        del sys.modules[m]
+    if SHIM not in sys.path:
+        sys.path.insert(0, SHIM)
+    tf = importlib.import_module("tensorflow")
+    tf.reset_default_graph()
+    return tf
+
+
+def run_reference_script(yuv_bytes: bytes, width: int, height: int, qp: int, thr_line: str = None) -> np.ndarray:
+    """Execute the unmodified video_to_cu_depth.py the way HM does (TAppEncCfg.cpp:2319) and return
+    the float32 contents of the cu_depth.dat it wrote."""
+    work = tempfile.mkdtemp(prefix="ethcnn_golden_")
+    old_cwd, old_argv, old_path = os.getcwd(), sys.argv, list(sys.path)
+    try:
+        for fn in os.listdir(AI_BIN):
+            if fn.startswith("model_") and not fn.endswith(".meta"):
+                os.symlink(os.path.join(AI_BIN, fn), os.path.join(work, fn))
+        if thr_line is None:
+            shutil.copy(os.path.join(AI_BIN, "Thr_info.txt"), os.path.join(work, "Thr_info.txt"))
+        else:
+            with open(os.path.join(work, "Thr_info.txt"), "w") as f:
+                f.write(thr_line)
+        with open(os.path.join(work, "in.yuv"), "wb") as f:
+            f.write(yuv_bytes)
+        os.chdir(work)
+        _fresh_tf()
+        for m in ("net_CNN",):
+            sys.modules.pop(m, None)
+        sys.path.insert(0, AI_BIN)
+        sys.argv = ["video_to_cu_depth.py", "in.yuv", str(width), str(height), str(qp)]
+        runpy.run_path(os.path.join(AI_BIN, "video_to_cu_depth.py"), run_name="__main__")
+        return np.fromfile(os.path.join(work, "cu_depth.dat"), dtype="<f4").reshape(-1, 21)
+    finally:
+        os.chdir(old_cwd)
+        sys.argv = old_argv
+        sys.path[:] = old_path
+        shutil.rmtree(work, ignore_errors=True)
+
+
+def run_reference_ldp_net(ctus: np.ndarray, qp: int) -> np.ndarray:
+    """ETH-CNN_Training_LDP/net_CTU64.py net() (unmodified) with the deployed LDP CNN checkpoint."""
+    old_path = list(sys.path)
+    try:
+        tf = _fresh_tf()
+        sys.modules.pop("net_CTU64", None)
+        sys.path.insert(0, LDP_TRAIN)
+        nt = importlib.import_module("net_CTU64")
+        x = tf.placeholder("float", [None, 64, 64, 1])
+        y_ = tf.placeholder("float", [None, 16])
+        qp_ph = tf.placeholder("float", [None, 1])
+        outs = nt.net(x, y_, qp_ph, 0, 0, 0.01, 0.9, 1000, 0.3, 0)
+        y64, y32, y16, opt_vars_all = outs[3], outs[4], outs[5], outs[-1]
+        sess = tf.Session()
+        tf.train.Saver(opt_vars_all).restore(sess, os.path.join(LDP_BIN, "model_LDP_2000000_qp22~37.dat"))
+        n = ctus.shape[0]
+        r = sess.run([y64, y32, y16], feed_dict={x: ctus.reshape(n, 64, 64, 1).astype(np.float32),
+                                                 y_: np.zeros((n, 16)), qp_ph: np.full((n, 1), qp)})
+        return np.concatenate(r, axis=1).astype(np.float32)
+    finally:
+        sys.path[:] = old_path
+        sys.modules.pop("net_CTU64", None)
+
+
+def run_reference_resi_cnn(ctus: np.ndarray) -> np.ndarray:
+    """HM-16.5_Test_LDP/bin/net_CNN_LSTM_one_step.py resi_cnn() (unmodified): the 448-vector."""
+    old_path, old_cwd = list(sys.path), os.getcwd()
+    work = tempfile.mkdtemp(prefix="ethcnn_golden_")
+    try:
+        # the module reads 'Thr_info.txt' from cwd at import time (net_CNN_LSTM_one_step.py:72, mode 'r+')
+        shutil.copy(os.path.join(LDP_BIN, "Thr_info.txt"), os.path.join(work, "Thr_info.txt"))
+        os.chdir(work)
+        tf = _fresh_tf()
+        for m in ("net_CNN_LSTM_one_step", "config"):
+            sys.modules.pop(m, None)
+        sys.path.insert(0, LDP_BIN)
+        nt = importlib.import_module("net_CNN_LSTM_one_step")
+        x = tf.placeholder("float", [None, 64, 64, 1])
+        vector, opt_vars = nt.resi_cnn(x)
+        sess = tf.Session()
+        tf.train.Saver(opt_vars).restore(sess, os.path.join(LDP_BIN, "model_LDP_2000000_qp22~37.dat"))
+        n = ctus.shape[0]
+        v = sess.run(vector, feed_dict={x: ctus.reshape(n, 64, 64, 1).astype(np.float32)})
+        return np.asarray(v, dtype=np.float32).reshape(n, 448)
+    finally:
+        os.chdir(old_cwd)
+        shutil.rmtree(work, ignore_errors=True)
+        sys.path[:] = old_path
+        for m in ("net_CNN_LSTM_one_step", "config"):
+            sys.modules.pop(m, None)
+
+
+def demo_ctus() -> np.ndarray:
+    d = np.fromfile(os.path.join(REF, "ETH-CNN_Training_AI", "Data", "AI_Test_5000.dat_shuffled"), dtype=np.uint8)
+    return d.reshape(5000, 4992)[:, :4096].reshape(5000, 64, 64)
+
+
+def mosaic(ctus: np.ndarray, rows: int, cols: int) -> np.ndarray:
+    return ctus[:rows * cols].reshape(rows, cols, 64, 64).transpose(0, 2, 1, 3).reshape(rows * 64, cols * 64)
+
+
+def yuv_from_luma(frames) -> bytes:
+    out = []
+    for fr in frames:
+        h, w = fr.shape
+        out.append(np.ascontiguousarray(fr, dtype=np.uint8).tobytes())
+        out.append(bytes([128]) * (w * h // 2))
+    return b"".join(out)
+
+
+QPS = (22, 27, 32, 37)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    real = demo_ctus()
+
+    # A. padding in both directions, two frames, procedural content
+    w, h = 200, 136
+    yuv = eo.synth_yuv(w, h, 2, seed0=100)
+    np.savez_compressed(os.path.join(OUT, "ai_pad_200x136_f2.npz"), yuv=np.frombuffer(yuv, np.uint8), width=w, height=h,
+                        qps=np.array(QPS), **{"prob_qp%d" % q: run_reference_script(yuv, w, h, q) for q in QPS})
+
+    # B. mosaic of real CTUs (realistic spread of probabilities)
+    luma = mosaic(real[:40], 5, 8)
+    yuv = yuv_from_luma([luma])
+    np.savez_compressed(os.path.join(OUT, "ai_mosaic_512x320.npz"), yuv=np.frombuffer(yuv, np.uint8), width=512, height=320,
+                        qps=np.array(QPS), **{"prob_qp%d" % q: run_reference_script(yuv, 512, 320, q) for q in QPS})
+
+    # C. gates: 64x64 "video" -- every frame is its own sub-batch of one CTU.
+    wq = eo.load_weights(os.path.join(AI_BIN, eo.ai_model_prefix(32)))
+    p = eo.net_forward(real[:2000], 32, wq)
+    g1_off = np.where(p[:, 0] <= 0.45)[0][:3]                                   # y64 small -> y32, y16 zeroed
+    g2_off = np.where((p[:, 0] > 0.55) & (p[:, 1:5].max(1) <= 0.45))[0][:3]     # y64 on, y32 all small -> y16 zeroed
+    both_on = np.where((p[:, 0] > 0.55) & (p[:, 1:5].max(1) > 0.55))[0][:3]
+    assert len(g1_off) == 3 and len(g2_off) == 3 and len(both_on) == 3
+    sel = np.concatenate([g1_off, g2_off, both_on])
+    flat = np.full((1, 64, 64), 128, np.uint8)
+    frames = list(real[sel]) + [flat[0]]
+    yuv = yuv_from_luma(frames)
+    np.savez_compressed(os.path.join(OUT, "ai_gates_64x64_f10.npz"), yuv=np.frombuffer(yuv, np.uint8), width=64, height=64,
+                        qps=np.array([32]), prob_qp32=run_reference_script(yuv, 64, 64, 32))
+
+    # C2. a frame with more than 1024 CTUs: 33 x 32 = 1056 -> sub-batches 1024 + 32; textured band at the
+    # top, flat elsewhere, so the second sub-batch is entirely gated while the first is not.
+    w, h = 2112, 2048
+    luma = np.full((h, w), 128, np.uint8)
+    luma[:128, :1024] = mosaic(real[100:132], 2, 16)
+    yuv = yuv_from_luma([luma])
+    np.savez_compressed(os.path.join(OUT, "ai_subbatch_2112x2048.npz"), yuv=np.frombuffer(yuv, np.uint8), width=w, height=h,
+                        qps=np.array([32]), prob_qp32=run_reference_script(yuv, w, h, 32))
+
+    # C3. non-default thresholds (tokens [1] and [3] are the ones the script reads)
+    luma = mosaic(real[200:212], 3, 4)
+    yuv = yuv_from_luma([luma, np.full_like(luma, 77)])
+    thr_line = "0.9 0.95 0.8 0.7 0.6 0.4"
+    np.savez_compressed(os.path.join(OUT, "ai_thr_256x192_f2.npz"), yuv=np.frombuffer(yuv, np.uint8), width=256, height=192,
+                        qps=np.array([27]), thr_line=np.array(thr_line), prob_qp27=run_reference_script(yuv, 256, 192, 27, thr_line))
+
+    # D. BASELINE config 1: 768x512, 1 frame, QP 32 -- input regenerated from the recipe at test time
+    w, h = 768, 512
+    yuv = eo.synth_yuv(w, h, 1, seed0=1)
+    np.savez_compressed(os.path.join(OUT, "ai_cfg1_768x512.npz"), width=w, height=h, seed0=1, n_frames=1,
+                        yuv_sha256=np.array(hashlib.sha256(yuv).hexdigest()), qps=np.array([32]),
+                        prob_qp32=run_reference_script(yuv, w, h, 32))
+
+    # E. LDP residual CNN (config 5 arithmetic): residue-like CTUs + a few real ones
+    resi = eo.frame_to_ctus(eo.synth_residue_frame(512, 256, 7))
+    ctus = np.concatenate([resi, eo.known_answer_ctus(), real[:6]])
+    np.savez_compressed(os.path.join(OUT, "ldp_ctus.npz"), ctus=ctus, qps=np.array([22, 37]),
+                        prob_qp22=run_reference_ldp_net(ctus, 22), prob_qp37=run_reference_ldp_net(ctus, 37),
+                        fc1_vector=run_reference_resi_cnn(ctus))
+
+    # F. raw-CTU AI vectors (ungated single sub-batch semantics are covered by C; these pin the net itself)
+    ctus = np.concatenate([eo.known_answer_ctus(), real[300:330]])
+    out = {}
+    for q in QPS:
+        yuv = yuv_from_luma(list(ctus))  # 64x64 frames
+        out["prob_qp%d" % q] = run_reference_script(yuv, 64, 64, q, "0.5 -1 0.5 -1 0.5 -1")  # gates always open
+    np.savez_compressed(os.path.join(OUT, "ai_ctus_ungated.npz"), ctus=ctus, qps=np.array(QPS), **out)
+    print("golden fixtures written to", OUT)
+    for fn in sorted(os.listdir(OUT)):
+        print("  %-32s %8d B" % (fn, os.path.getsize(os.path.join(OUT, fn))))
+
+
+if __name__ == "__main__":
+    main()
