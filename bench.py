@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""bench.py -- CTUs/sec of the ETH-CNN CU-partition predictor (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE config 2 -- synthetic 1920x1080 8-bit 4:2:0, 50 frames per rank,
+QP cycling over {22, 27, 32, 37} step by step (one deployed checkpoint per QP range).  One "step" = one
+pass of the hot path over one 50-frame clip per rank (25 500 CTUs per rank).  With N ranks the sequence
+is N x 50 frames sharded in contiguous frame ranges (weak scaling) and every step ends with the NCCL
+gather of the per-rank cu_depth rows to rank 0.
+
+  value  device-resident: luma already in HBM, kernels + gather, CUDA events, max over ranks
+  e2e    the public host API (ethcnn_predict_luma through ctypes) from PINNED HOST memory: H2D of the
+         luma planes, kernels, D2H of the probabilities (+ gather), every step
+  roofline       dominant kernel: algorithmic bytes (or FLOPs) of its launches / its CUDA-event time
+  cpu_baseline   the oracle port of the reference's script on the host cores (rank 0, N = 1, bounded)
+
+--impl reference times that CPU port alone (the reference's TensorFlow cannot be installed here).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, FRAMES = 1920, 1080, 50
+QPS = (22, 27, 32, 37)
+CTUS_PER_FRAME = 30 * 17
+ALG_BYTES_PER_CTU = 4096 + 84
+ALG_FLOP_PER_CTU = 3104298              # 2 * 1 552 149 MAC
+FC1_FLOP_PER_CTU = 2 * 1204224
+CONV_FLOP_PER_CTU = 2 * 279552
+FP32_FFMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal, not measured
+
+
+def make_clip(seed0: int, n_base: int = 5) -> np.ndarray:
+    """50 luma frames [50, H, W] uint8: a few procedural frames (oracle.synth_frame) and shifted copies."""
+    from oracle import ethcnn_oracle as eo
+
+    base = [eo.synth_frame(W, H, seed0 + k) for k in range(n_base)]
+    out = np.empty((FRAMES, H, W), dtype=np.uint8)
+    for k in range(FRAMES):
+        out[k] = np.roll(base[k % n_base], shift=(8 * (k // n_base), 16 * (k // n_base)), axis=(0, 1))
+    return out
+
+
+def prepare_models():
+    """Directory with the four AI checkpoints (deployed ones when the box has them, synthetic otherwise)."""
+    from oracle import assets, tf_bundle
+    from oracle import ethcnn_oracle as eo
+
+    d = tempfile.mkdtemp(prefix="ethcnn_bench_")
+    present = assets.materialize(d, "AI")
+    synthetic = []
+    for qp, name in assets.AI_MODELS.items():
+        if name not in present:
+            tf_bundle.write_bundle(os.path.join(d, name), eo.random_weights(100 + qp))
+            synthetic.append(qp)
+    return d, synthetic
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.remove(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = sorted(sm)[len(sm) // 2:]  # upper half = samples under load
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+_POOL_W = {}
+
+
+def _pool_init(model_dir):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    from oracle import assets, tf_bundle
+    for qp, name in assets.AI_MODELS.items():
+        _POOL_W[qp] = tf_bundle.read_bundle(os.path.join(model_dir, name))
+
+
+def _pool_frame(args):
+    from oracle import ethcnn_oracle as eo
+    luma, qp = args
+    vh, vw = -(-H // 64) * 64, -(-W // 64) * 64
+    pad = np.zeros((vh, vw), np.uint8)
+    pad[:H, :W] = luma
+    return eo.predict_frame(pad, qp, _POOL_W[qp], eo.MODE_AI, (0.5, 0.5))
+
+
+class CpuReference(object):
+    """The oracle port run the reference's way (per frame: pad, slice 64x64 CTUs in raster order, sub-batches
+    of <= 1024 through the fp32 net, gates), frames farmed out to one worker process per host core."""
+
+    def __init__(self, model_dir):
+        import multiprocessing as mp
+        from concurrent.futures import ProcessPoolExecutor
+
+        self.cores = os.cpu_count() or 1
+        self.pool = ProcessPoolExecutor(max_workers=self.cores, mp_context=mp.get_context("fork"),
+                                        initializer=_pool_init, initargs=(model_dir,))
+        list(self.pool.map(_pool_frame, [(np.zeros((H, W), np.uint8), 32)] * self.cores))  # start the workers
+
+    def run(self, frames: np.ndarray, qp: int) -> np.ndarray:
+        return np.concatenate(list(self.pool.map(_pool_frame, [(f, qp) for f in frames])), axis=0)
+
+    def close(self):
+        self.pool.shutdown()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    model_dir, synthetic = prepare_models()
+    ref = CpuReference(model_dir)
+    clip = make_clip(0)
+    # bounded sample: size the per-step frame count so that steps+warmup finish in a couple of minutes
+    t = time.time()
+    ref.run(clip[:ref.cores], 32)
+    per_frame = (time.time() - t) / ref.cores
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    n = int(max(1, min(FRAMES, budget / max(per_frame, 1e-6))))
+    for i in range(args.warmup):
+        ref.run(clip[:n], QPS[i % 4])
+    t0 = time.time()
+    for i in range(args.steps):
+        ref.run(clip[:n], QPS[i % 4])
+    dt = time.time() - t0
+    ref.close()
+    v = args.steps * n * CTUS_PER_FRAME / dt
+    line = {
+        "impl": "reference", "metric": "CTUs/sec (ETH-CNN inference)", "value": v, "unit": "CTU/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "config2: 1920x1080 4:2:0, QP cycling 22/27/32/37", "frames_per_step": n,
+                   "note": "TensorFlow is not installable here: this is the oracle port of video_to_cu_depth.py/net_CNN.py "
+                           "(numpy fp32, per-frame CTU slicing, sub-batches of 1024, gates), one worker process per core"},
+        "cpu_baseline": {"value": v, "unit": "CTU/s", "cores": ref.cores, "kind": "port",
+                         "sample": "%d frames of 1920x1080 per step, %d steps" % (n, args.steps)},
+        "e2e": {"value": v, "unit": "CTU/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import ethcnn_b200 as eb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun (one rank per GPU)" % args.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    model_dir, synthetic = prepare_models()
+    net = eb.EthCnn(model_dir, None, eb.MODE_AI, device=local)
+    n_ctus = FRAMES * CTUS_PER_FRAME
+
+    # one clip per QP (4 x 103.7 MB of luma > 126 MB L2, so a step never finds its input in L2)
+    clips_host, clips_dev = [], []
+    for i, qp in enumerate(QPS):
+        c = torch.from_numpy(make_clip(1000 * rank + 10 * i)).pin_memory()
+        clips_host.append(c)
+        clips_dev.append(c.to(dev))
+    out_dev = torch.empty((n_ctus, 21), dtype=torch.float32, device=dev)
+    out_host = torch.empty((n_ctus, 21), dtype=torch.float32).pin_memory()
+    gather_buf = [torch.empty_like(out_dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(i):
+        k = i % 4
+        net.predict_luma_device(clips_dev[k].data_ptr(), W, H, W, W * H, FRAMES, QPS[k], out_dev.data_ptr(), stream.cuda_stream)
+        if world > 1:
+            dist.gather(out_dev, gather_buf, dst=0)
+
+    def step_e2e(i):
+        k = i % 4
+        net.predict_luma_ptr(clips_host[k].data_ptr(), W, H, W * H, FRAMES, QPS[k], out_host.data_ptr())
+        if world > 1:
+            out_dev.copy_(out_host, non_blocking=True)
+            dist.gather(out_dev, gather_buf, dst=0)
+            if rank == 0:
+                torch.cat(gather_buf).cpu()
+
+    def timed(step_fn, steps, warmup):
+        for i in range(warmup):
+            step_fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for i in range(steps):
+            step_fn(i)
+        e1.record(stream)
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        dev_ms = e0.elapsed_time(e1)
+        return dev_ms, wall_ms
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- device-resident (kernel) number, with per-stage events
+    net.profile_enable(True)
+    for s in range(4):
+        net.profile_read(s, reset=True)
+    sampler = ClockSampler(local)
+    launches0 = net.kernel_launches
+    # warm-up outside the profile window
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+    for s in range(4):
+        net.profile_read(s, reset=True)
+    launches0 = net.kernel_launches
+    sampler.start()
+    dev_ms, _ = timed(step_device, args.steps, 0)
+    clocks = sampler.stop()
+    launches = net.kernel_launches - launches0
+    stage = {}
+    for s, name in enumerate(eb.STAGE_NAMES):
+        ms, n = net.profile_read(s, reset=True)
+        stage[name] = {"ms_total": ms, "launches": n}
+    net.profile_enable(False)
+    dev_ms = max_over_ranks(dev_ms)
+    value = world * args.steps * n_ctus / (dev_ms * 1e-3)
+
+    # ---- end to end through the host API (pinned host buffers; H2D + kernels + D2H inside the timed region)
+    # the device timeline cannot see host work, so e2e is wall clock between synchronised barriers, max over ranks
+    _, e2e_wall_ms = timed(step_e2e, args.steps, max(3, args.warmup))
+    e2e_ms = max_over_ranks(e2e_wall_ms)
+    e2e_value = world * args.steps * n_ctus / (e2e_ms * 1e-3)
+    total_launches = int(sum_over_ranks(launches))
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        tf_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+        peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+        ctus_timed = args.steps * n_ctus
+        dom = max(("conv", "fc1", "heads"), key=lambda k: stage[k]["ms_total"])
+        per_stage = {}
+        for name in ("conv", "fc1", "heads", "gate"):
+            ms = stage[name]["ms_total"]
+            per_stage[name] = {"ms_per_step": ms / args.steps, "launches_per_step": stage[name]["launches"] / args.steps,
+                               "share_of_kernel_time": ms / max(1e-9, sum(v["ms_total"] for v in stage.values()))}
+        fc1_s = stage["fc1"]["ms_total"] * 1e-3
+        conv_s = stage["conv"]["ms_total"] * 1e-3
+        dom_s = stage[dom]["ms_total"] * 1e-3
+        # dominant kernel against the HBM roofline with the path's algorithmic bytes (north_star: "fraction of the
+        # HBM-read roofline"); the tensor-core and fp32 views of FC1 / conv are reported beside it
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": ctus_timed * ALG_BYTES_PER_CTU / dom_s / 1e9, "peak": hbm_peak,
+                    "unit": "GB/s", "traffic": None, "peak_source": peak_src,
+                    "avg_launch_ms": stage[dom]["ms_total"] / max(1, stage[dom]["launches"])}
+        roofline["frac"] = roofline["achieved"] / roofline["peak"]
+        roofline_fc1 = {"kernel": "fc1", "bound": "tensor", "achieved": ctus_timed * FC1_FLOP_PER_CTU / fc1_s / 1e12,
+                        "peak": tf_peak, "unit": "TFLOP/s", "peak_source": peak_src,
+                        "note": "algorithmic FLOPs; the kernel issues 3x this in fp16 (hi/lo split passes)"}
+        roofline_fc1["frac"] = roofline_fc1["achieved"] / tf_peak
+        roofline_conv = {"kernel": "conv", "bound": "fp32-ffma", "achieved": ctus_timed * CONV_FLOP_PER_CTU / conv_s / 1e12,
+                         "peak": FP32_FFMA_PEAK_TFLOPS, "unit": "TFLOP/s", "peak_source": "nominal 148 SM x 128 FMA x 1.965 GHz"}
+        roofline_conv["frac"] = roofline_conv["achieved"] / FP32_FFMA_PEAK_TFLOPS
+        whole = {"hbm_frac": value * ALG_BYTES_PER_CTU / 1e9 / hbm_peak, "tensor_frac": value / world * ALG_FLOP_PER_CTU / 1e12 / tf_peak}
+
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            ref = CpuReference(model_dir)
+            clip = clips_host[2].numpy()
+            t = time.time()
+            ref.run(clip[:ref.cores], 32)
+            per_frame = (time.time() - t) / ref.cores
+            n = int(max(ref.cores, min(FRAMES, 15.0 / max(per_frame, 1e-6))))
+            t = time.time()
+            ref.run(clip[:n], 32)
+            dt = time.time() - t
+            cpu_baseline = {"value": n * CTUS_PER_FRAME / dt, "unit": "CTU/s", "cores": ref.cores, "kind": "port",
+                            "sample": "%d frames of 1920x1080 at QP 32 (oracle port, one worker process per core)" % n}
+            ref.close()
+
+        line = {
+            "metric": "CTUs/sec (ETH-CNN inference)", "value": value, "unit": "CTU/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (convs fp32 FFMA; FC1 3-pass split-fp16 tcgen05 with fp32 accumulate)",
+            "data": "synthetic luma; weights: %s" % ("deployed checkpoints" if not synthetic else
+                                                     "synthetic checkpoints for QP %s" % synthetic),
+            "config": {"workload": "config2: 1920x1080 4:2:0, 50 frames per rank per step, QP cycling 22/27/32/37",
+                       "ctus_per_step": world * n_ctus, "sharding": "contiguous frame ranges, NCCL gather to rank 0" if world > 1 else "single GPU",
+                       "l2": "inputs rotate over 4 clips (415 MB luma) + ~600 MB of scratch traffic per step, larger than the 126 MB L2",
+                       "fc1_path": "tcgen05" if net.query(3) == 1 else "simt"},
+            "e2e": {"value": e2e_value, "unit": "CTU/s", "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": world * FRAMES * W * H, "d2h_bytes_per_step": world * n_ctus * 84,
+                    "timing": "wall clock between device-synchronised barriers, max over ranks"},
+            "gpu_launches": total_launches,
+            "clocks": clocks,
+            "roofline": roofline,
+            "roofline_fc1": roofline_fc1,
+            "roofline_conv": roofline_conv,
+            "whole_path_fraction": whole,
+            "stages": per_stage,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line))
+    net.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

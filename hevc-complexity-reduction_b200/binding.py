@@ -1,0 +1,213 @@
+"""ctypes binding of libethcnn_b200.so -- exactly the stub a maintainer of the reference would add
+(see INTEGRATION.md).  Signatures follow include/ethcnn.h one to one."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+MODE_AI = 0
+MODE_LDP = 1
+PROBS_PER_CTU = 21
+FC1_WIDTH = 448
+STAGE_CONV, STAGE_FC1, STAGE_HEADS, STAGE_GATE = 0, 1, 2, 3
+STAGE_NAMES = ("conv", "fc1", "heads", "gate")
+
+Q_KERNEL_LAUNCHES, Q_N_DEVICES, Q_FC1_PATH, Q_TMA_LOADER_USED, Q_SM_COUNT = 1, 2, 3, 4, 5
+OPT_FC1_PATH, OPT_CHUNK_CTUS = 1, 2
+
+_LIB = None
+
+
+class EthCnnError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__("ethcnn error %d: %s" % (code, message))
+        self.code = code
+
+
+def library_path() -> str:
+    return os.environ.get("ETHCNN_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libethcnn_b200.so")
+
+
+def load_library() -> C.CDLL:
+    """Load the CUDA extension; fails loudly (no fallback) when it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise EthCnnError(-2, "%s not found -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "or `make -C hevc-complexity-reduction_b200`; there is no CPU fallback" % path)
+    lib = C.CDLL(path)
+    vp, cp, i32, i64, sz = C.c_void_p, C.c_char_p, C.c_int, C.c_int64, C.c_size_t
+    sig = {
+        "ethcnn_abi_version": (i32, []),
+        "ethcnn_last_error": (cp, []),
+        "ethcnn_create": (i32, [cp, cp, i32, i32, C.POINTER(vp)]),
+        "ethcnn_create_on_device": (i32, [cp, cp, i32, i32, C.POINTER(vp)]),
+        "ethcnn_destroy": (None, [vp]),
+        "ethcnn_predict_yuv_file": (i32, [vp, cp, i32, i32, i32, cp]),
+        "ethcnn_predict_luma": (i32, [vp, vp, i32, i32, sz, i32, i32, vp]),
+        "ethcnn_predict_luma_device": (i32, [vp, vp, i32, i32, sz, sz, i32, i32, vp, vp]),
+        "ethcnn_export_fc1": (i32, [vp, vp, i32, i32, sz, i32, vp]),
+        "ethcnn_decisions": (i32, [vp, vp, sz, vp, vp]),
+        "ethcnn_query": (i32, [vp, i32, C.POINTER(i64)]),
+        "ethcnn_profile_enable": (i32, [vp, i32]),
+        "ethcnn_profile_read": (i32, [vp, i32, C.POINTER(C.c_double), C.POINTER(i64), i32]),
+        "ethcnn_set_option": (i32, [vp, i32, i64]),
+        "ethcnn_alloc_pinned": (vp, [sz]),
+        "ethcnn_free_pinned": (None, [vp]),
+        "ethcnn_debug_pack_model": (i32, [cp, C.c_float, vp, vp, vp, vp, vp, vp, vp]),
+        "ethcnn_debug_read_thresholds": (i32, [cp, vp]),
+        "ethcnn_debug_f32_to_f16": (C.c_uint16, [C.c_float]),
+        "ethcnn_debug_read_scratch": (i32, [vp, i32, sz, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise EthCnnError(rc, load_library().ethcnn_last_error().decode("utf-8", "replace"))
+
+
+def ctu_grid(width: int, height: int) -> Tuple[int, int]:
+    """(rows, cols) of 64x64 CTUs after the reference's zero padding (video_to_cu_depth.py:52-57)."""
+    return math.ceil(height / 64), math.ceil(width / 64)
+
+
+def _ptr(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data)
+
+
+class EthCnn(object):
+    """One predictor instance (weights resident on the device across calls).
+
+    Mirrors the module-level state of video_to_cu_depth.py:14-29 (session + saver) and
+    net_CNN.py:47 (thresholds read from Thr_info.txt)."""
+
+    def __init__(self, model_dir: str = ".", thr_path: Optional[str] = None, mode: int = MODE_AI, n_gpus: int = 1,
+                 device: Optional[int] = None):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        md = os.fsencode(model_dir)
+        tp = os.fsencode(thr_path) if thr_path is not None else None
+        if device is None:
+            _check(self._lib.ethcnn_create(md, tp, mode, n_gpus, C.byref(self._h)))
+        else:
+            _check(self._lib.ethcnn_create_on_device(md, tp, mode, device, C.byref(self._h)))
+        self.mode = mode
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.ethcnn_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+        return False
+
+    # --- the reference's script as a call (video_to_cu_depth.py:120-145)
+    def predict_yuv_file(self, yuv_path: str, width: int, height: int, qp: int, out_path: str = "cu_depth.dat") -> None:
+        _check(self._lib.ethcnn_predict_yuv_file(self._h, os.fsencode(yuv_path), width, height, qp, os.fsencode(out_path)))
+
+    # --- get_prob() for luma in host memory (video_to_cu_depth.py:75-118)
+    def predict_yuv_buffer(self, yuv: np.ndarray, width: int, height: int, qp: int) -> np.ndarray:
+        """yuv: uint8 array holding whole 4:2:0 frames (Y, U, V planar).  Returns float32 [n_frames*nCTU, 21]."""
+        yuv = np.ascontiguousarray(yuv, dtype=np.uint8).reshape(-1)
+        frame_bytes = width * height * 3 // 2
+        if yuv.size % frame_bytes != 0:
+            raise EthCnnError(-1, "file_bytes % frame_bytes != 0")  # video_to_cu_depth.py:137
+        return self.predict_luma(yuv, width, height, yuv.size // frame_bytes, qp, frame_stride=frame_bytes)
+
+    def predict_luma(self, y: np.ndarray, width: int, height: int, n_frames: int, qp: int,
+                     frame_stride: Optional[int] = None, out: Optional[np.ndarray] = None) -> np.ndarray:
+        y = np.ascontiguousarray(y, dtype=np.uint8)
+        if frame_stride is None:
+            frame_stride = width * height
+        need = (n_frames - 1) * frame_stride + width * height if n_frames > 0 else 0
+        if y.size < need:
+            raise EthCnnError(-1, "luma buffer too small")
+        r, c = ctu_grid(width, height)
+        if out is None:
+            out = np.empty((n_frames * r * c, PROBS_PER_CTU), dtype=np.float32)
+        _check(self._lib.ethcnn_predict_luma(self._h, _ptr(y), width, height, frame_stride, n_frames, qp, _ptr(out)))
+        return out
+
+    def predict_luma_ptr(self, y_ptr: int, width: int, height: int, frame_stride: int, n_frames: int, qp: int, out_ptr: int):
+        """Raw host-pointer form (pinned buffers owned by the caller, e.g. torch pinned tensors)."""
+        _check(self._lib.ethcnn_predict_luma(self._h, C.c_void_p(y_ptr), width, height, frame_stride, n_frames, qp,
+                                             C.c_void_p(out_ptr)))
+
+    def predict_luma_device(self, d_y: int, width: int, height: int, pitch: int, frame_stride: int, n_frames: int, qp: int,
+                            d_out: int, stream: int = 0) -> None:
+        """Device pointers (ints), asynchronous on `stream` (a cudaStream_t value)."""
+        _check(self._lib.ethcnn_predict_luma_device(self._h, C.c_void_p(d_y), width, height, pitch, frame_stride, n_frames,
+                                                    qp, C.c_void_p(d_out), C.c_void_p(stream)))
+
+    def predict_ctus(self, ctus: np.ndarray, qp: int) -> np.ndarray:
+        """ctus: uint8 [n, 64, 64].  Each CTU is treated as its own 64x64 frame, i.e. its own sub-batch of one
+        (the reference run on a 64x64 'video'); returns float32 [n, 21]."""
+        ctus = np.ascontiguousarray(ctus, dtype=np.uint8).reshape(-1, 64 * 64)
+        return self.predict_luma(ctus, 64, 64, ctus.shape[0], qp)
+
+    def export_fc1(self, y: np.ndarray, width: int, height: int, n_frames: int, frame_stride: Optional[int] = None) -> np.ndarray:
+        """LDP FC1 tap (net_CNN_LSTM_one_step.py:151-199): float32 [n_frames*nCTU, 448]."""
+        y = np.ascontiguousarray(y, dtype=np.uint8)
+        if frame_stride is None:
+            frame_stride = width * height
+        r, c = ctu_grid(width, height)
+        out = np.empty((n_frames * r * c, FC1_WIDTH), dtype=np.float32)
+        _check(self._lib.ethcnn_export_fc1(self._h, _ptr(y), width, height, frame_stride, n_frames, _ptr(out)))
+        return out
+
+    def decisions(self, prob: np.ndarray, thr6=(0.5,) * 6) -> np.ndarray:
+        """HM's threshold rule on the device (TEncCu.cpp:448-462): uint8 array shaped like prob."""
+        prob = np.ascontiguousarray(prob, dtype=np.float32).reshape(-1, PROBS_PER_CTU)
+        thr = np.asarray(thr6, dtype=np.float32)
+        out = np.empty(prob.shape, dtype=np.uint8)
+        _check(self._lib.ethcnn_decisions(self._h, _ptr(prob), prob.shape[0], _ptr(thr), _ptr(out)))
+        return out
+
+    def debug_read_scratch(self, what: int, n_ctus: int) -> np.ndarray:
+        """Testing hook: intermediates of the last chunk (0 = conv features [n,2688], 1 = FC1 [n,448])."""
+        out = np.empty((n_ctus, 2688 if what == 0 else FC1_WIDTH), dtype=np.float32)
+        _check(self._lib.ethcnn_debug_read_scratch(self._h, what, n_ctus, _ptr(out)))
+        return out
+
+    # --- introspection / tuning
+    def query(self, what: int) -> int:
+        v = C.c_int64()
+        _check(self._lib.ethcnn_query(self._h, what, C.byref(v)))
+        return int(v.value)
+
+    @property
+    def kernel_launches(self) -> int:
+        return self.query(Q_KERNEL_LAUNCHES)
+
+    def set_option(self, option: int, value: int) -> None:
+        _check(self._lib.ethcnn_set_option(self._h, option, value))
+
+    def profile_enable(self, on: bool = True) -> None:
+        _check(self._lib.ethcnn_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self, stage: int, reset: bool = False) -> Tuple[float, int]:
+        ms, n = C.c_double(), C.c_int64()
+        _check(self._lib.ethcnn_profile_read(self._h, stage, C.byref(ms), C.byref(n), 1 if reset else 0))
+        return float(ms.value), int(n.value)

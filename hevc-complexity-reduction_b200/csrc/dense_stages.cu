@@ -1,0 +1,230 @@
+// Stages FC1 (SIMT fp32 variant), HEADS, GATE and the HM decision quantiser (sm_100a).
+//   FC1   : net_CNN.py:156,166,178   a1 = leaky(f W1 + b1), the three heads side by side (448 columns)
+//   HEADS : net_CNN.py:158-163,168-173,180-185   a2 = leaky([a1,q] W2 + b2); y = sigmoid([a2,q] W3 + b3)
+//   GATE  : net_CNN.py:175,187 over each <=1024-CTU sub-batch of one frame (video_to_cu_depth.py:64-70)
+//   decisions: TLibEncoder/TEncCu.cpp:448-462
+#include "kernels.h"
+
+namespace ethcnn {
+namespace {
+
+__device__ __forceinline__ float leaky(float v) { return fmaxf(0.2f * v, v); }
+
+// ------------------------------------------------------------------------------------------------
+// FC1, SIMT fp32: C[n][448] = leaky(A[n][2688] * W[2688][448] + b), A rebuilt from its hi/lo halves.
+// 64 x 64 output tile per CTA, 256 threads, 4 x 4 outputs per thread, K tile 16.
+constexpr int kSB = 64, kSK = 16;
+
+__global__ void __launch_bounds__(256) fc1_simt_kernel(const __half* __restrict__ fhi, const __half* __restrict__ flo,
+                                                       float inv_scale, const float* __restrict__ w1,
+                                                       const float* __restrict__ b1, float* __restrict__ out, int n) {
+  __shared__ float As[kSK][kSB + 4];
+  __shared__ float Bs[kSK][kSB];
+  const int row0 = blockIdx.x * kSB, col0 = blockIdx.y * kSB;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  // loader mapping: A tile 64 rows x 16 k -> thread loads 4 consecutive k of one row (8 bytes of hi, of lo)
+  const int ar = threadIdx.x >> 2, ak = (threadIdx.x & 3) * 4;
+  // B tile 16 k x 64 cols -> thread loads 4 consecutive cols of one k row
+  const int bk = threadIdx.x >> 4, bc = (threadIdx.x & 15) * 4;
+
+  for (int k0 = 0; k0 < kFeat; k0 += kSK) {
+    {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      const int r = row0 + ar;
+      if (r < n) {
+        const uint2 h = *reinterpret_cast<const uint2*>(fhi + size_t(r) * kFeat + k0 + ak);
+        const uint2 l = *reinterpret_cast<const uint2*>(flo + size_t(r) * kFeat + k0 + ak);
+        const __half2 h0 = *reinterpret_cast<const __half2*>(&h.x), h1 = *reinterpret_cast<const __half2*>(&h.y);
+        const __half2 l0 = *reinterpret_cast<const __half2*>(&l.x), l1 = *reinterpret_cast<const __half2*>(&l.y);
+        v[0] = (__low2float(h0) + __low2float(l0)) * inv_scale;
+        v[1] = (__high2float(h0) + __high2float(l0)) * inv_scale;
+        v[2] = (__low2float(h1) + __low2float(l1)) * inv_scale;
+        v[3] = (__high2float(h1) + __high2float(l1)) * inv_scale;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) As[ak + i][ar] = v[i];
+      const float4 w = *reinterpret_cast<const float4*>(w1 + size_t(k0 + bk) * kFc1 + col0 + bc);
+      *reinterpret_cast<float4*>(&Bs[bk][bc]) = w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kSK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const float4 bias = *reinterpret_cast<const float4*>(b1 + col0 + tx * 4);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = row0 + ty * 4 + i;
+    if (r < n) {
+      float4 o;
+      o.x = leaky(acc[i][0] + bias.x), o.y = leaky(acc[i][1] + bias.y);
+      o.z = leaky(acc[i][2] + bias.z), o.w = leaky(acc[i][3] + bias.w);
+      *reinterpret_cast<float4*>(out + size_t(r) * kFc1 + col0 + tx * 4) = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// HEADS: one CTA = 32 CTUs of one head.  Thread j < N2 owns FC2 output column j for all 32 CTUs
+// (weights streamed once through registers, activations broadcast from shared memory), then the
+// 32 x N3 FC3 dot products are spread over the block.
+constexpr int kHT = 32;  // CTUs per CTA
+
+template <int N1, int N2, int N3, int OUT_OFF, int COL_OFF>
+__device__ __forceinline__ void heads_body(const HeadsLaunch& p, const HeadWeights& w, float* smem) {
+  const int NT = blockDim.x;       // every thread of the CTA takes part in the loads and barriers
+  float* a1s = smem;               // [N1][32]
+  float* a2s = smem + N1 * kHT;    // [N2][33]
+  const int n0 = blockIdx.x * kHT;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < (N1 / 4) * kHT; i += NT) {
+    const int c = i % kHT, k4 = i / kHT;  // CTU fastest: conflict-free transposed store
+    const int n = n0 + c;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < p.n_ctus) v = *reinterpret_cast<const float4*>(p.fc1 + size_t(n) * kFc1 + COL_OFF + 4 * k4);
+    a1s[(4 * k4 + 0) * kHT + c] = v.x;
+    a1s[(4 * k4 + 1) * kHT + c] = v.y;
+    a1s[(4 * k4 + 2) * kHT + c] = v.z;
+    a1s[(4 * k4 + 3) * kHT + c] = v.w;
+  }
+  __syncthreads();
+  if (tid < N2) {
+    float acc[kHT];
+    const float init = fmaf(p.q, w.w2q[tid], w.b2[tid]);
+#pragma unroll
+    for (int c = 0; c < kHT; ++c) acc[c] = init;
+#pragma unroll 4
+    for (int k = 0; k < N1; ++k) {
+      const float wv = __ldg(w.w2 + k * N2 + tid);
+      const float4* a = reinterpret_cast<const float4*>(a1s + k * kHT);
+#pragma unroll
+      for (int c4 = 0; c4 < kHT / 4; ++c4) {
+        const float4 v = a[c4];
+        acc[4 * c4] = fmaf(v.x, wv, acc[4 * c4]);
+        acc[4 * c4 + 1] = fmaf(v.y, wv, acc[4 * c4 + 1]);
+        acc[4 * c4 + 2] = fmaf(v.z, wv, acc[4 * c4 + 2]);
+        acc[4 * c4 + 3] = fmaf(v.w, wv, acc[4 * c4 + 3]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < kHT; ++c) a2s[tid * (kHT + 1) + c] = leaky(acc[c]);
+  }
+  __syncthreads();
+  for (int i = tid; i < kHT * N3; i += NT) {
+    const int o = i / kHT, c = i - o * kHT;
+    const int n = n0 + c;
+    float acc = fmaf(p.q, w.w3q[o], w.b3[o]);
+    for (int j = 0; j < N2; ++j) acc = fmaf(a2s[j * (kHT + 1) + c], __ldg(w.w3 + j * N3 + o), acc);
+    const float y = 1.0f / (1.0f + expf(-acc));
+    if (n < p.n_ctus) {
+      const int gn = p.ctu_begin + n;
+      p.prob[size_t(gn) * kProbs + OUT_OFF + o] = y;
+      if (p.flags != nullptr && N3 <= 4) {
+        const float thr = (N3 == 1) ? p.t1 : p.t2;
+        if (y > thr) {
+          const unsigned bit = (N3 == 1) ? 1u : 2u;
+          const int f = gn / p.ctus_per_frame, r = gn - f * p.ctus_per_frame;
+          unsigned* fl = p.flags + f * p.chunks_per_frame + r / kSubBatch;
+          if (!(*reinterpret_cast<volatile unsigned*>(fl) & bit)) atomicOr(fl, bit);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(192) heads_kernel(const HeadsLaunch p) {
+  extern __shared__ __align__(16) float hsm[];
+  // blockIdx.y selects the head (warp-uniform); threads beyond a head's FC2 width only help with loads.
+  if (blockIdx.y == 0) {
+    heads_body<64, 48, 1, 0, 0>(p, p.head[0], hsm);
+  } else if (blockIdx.y == 1) {
+    heads_body<128, 96, 4, 1, 64>(p, p.head[1], hsm);
+  } else {
+    heads_body<256, 192, 16, 5, 192>(p, p.head[2], hsm);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GATE (AI deployment): per sub-batch  g1 = any(y64 > t1);  y32 := g1 ? y32 : 0;
+//                                      g2 = any(y32_gated > t2);  y16 := g2 ? y16 : 0.
+// When g1 is false the gated y32 is all zeros, so g2 = (0 > t2).
+__global__ void gate_kernel(float* __restrict__ prob, const unsigned* __restrict__ flags, float t2, long long n_total,
+                            int ctus_per_frame, int chunks_per_frame) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // one thread per (CTU, slot 1..20)
+  if (i >= n_total * 20) return;
+  const long long n = i / 20;
+  const int slot = 1 + int(i - n * 20);
+  const long long f = n / ctus_per_frame;
+  const int r = int(n - f * ctus_per_frame);
+  const unsigned fl = flags[f * chunks_per_frame + r / kSubBatch];
+  const bool g1 = (fl & 1u) != 0;
+  const bool g2 = g1 ? ((fl & 2u) != 0) : (0.0f > t2);
+  const bool keep = (slot < 5) ? g1 : g2;
+  if (!keep) prob[n * kProbs + slot] = 0.0f;
+}
+
+__global__ void decisions_kernel(const float* __restrict__ prob, unsigned char* __restrict__ dec, long long n_values,
+                                 const float* __restrict__ thr6) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n_values) return;
+  const int slot = int(i % kProbs);
+  const int lvl = slot == 0 ? 0 : (slot < 5 ? 1 : 2);
+  const float up = thr6[2 * lvl], down = thr6[2 * lvl + 1];
+  const float p = prob[i];
+  dec[i] = (p > up) ? 2 : ((p <= down) ? 0 : 1);  // TEncCu.cpp:448-457: "> up" split only, "<= down" no split
+}
+
+}  // namespace
+
+cudaError_t launch_fc1_simt(const __half* feat_hi, const __half* feat_lo, float inv_feat_scale, const float* w1,
+                            const float* b1, float* fc1_out, int n_ctus, cudaStream_t stream) {
+  if (n_ctus <= 0) return cudaSuccess;
+  dim3 grid((n_ctus + kSB - 1) / kSB, kFc1 / kSB);
+  fc1_simt_kernel<<<grid, 256, 0, stream>>>(feat_hi, feat_lo, inv_feat_scale, w1, b1, fc1_out, n_ctus);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_heads(const HeadsLaunch& p, cudaStream_t stream) {
+  if (p.n_ctus <= 0) return cudaSuccess;
+  static bool configured = false;
+  constexpr int smem = (256 * kHT + 192 * (kHT + 1)) * 4;  // 58112 B
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((p.n_ctus + kHT - 1) / kHT, 3);
+  heads_kernel<<<grid, 192, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gate(float* prob, const unsigned* flags, float t2, long long n_total, int ctus_per_frame,
+                        int chunks_per_frame, cudaStream_t stream) {
+  if (n_total <= 0) return cudaSuccess;
+  const long long work = n_total * 20;
+  gate_kernel<<<unsigned((work + 255) / 256), 256, 0, stream>>>(prob, flags, t2, n_total, ctus_per_frame, chunks_per_frame);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_decisions(const float* prob, unsigned char* dec, long long n_values, const float* thr6_dev,
+                             cudaStream_t stream) {
+  if (n_values <= 0) return cudaSuccess;
+  decisions_kernel<<<unsigned((n_values + 255) / 256), 256, 0, stream>>>(prob, dec, n_values, thr6_dev);
+  return cudaGetLastError();
+}
+
+}  // namespace ethcnn

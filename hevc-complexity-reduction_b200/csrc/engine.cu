@@ -1,0 +1,847 @@
+// Host engine + C ABI of libethcnn_b200.so (see include/ethcnn.h for the contract and the reference
+// interfaces each entry point replaces).
+//
+// Data flow for one call (per device):
+//   host luma --H2D (copy stream, slabs of whole frames, Y only)--> device slab [frames][H][pitch16]
+//   CONV kernel (TMA tiles) -> features fp16 hi/lo [chunk][2688]  (scratch, chunk = 18944 CTUs)
+//   FC1 kernel -> [chunk][448] fp32 -> HEADS kernel -> raw probabilities + gate flags
+//   GATE kernel over the slab -> D2H of 84 B/CTU into the caller's buffer (its frame range = the "gather")
+// Slabs are double-buffered so copies overlap kernels.  With n_gpus > 1 one host thread per device
+// runs the same pipeline on a contiguous frame range (video_to_cu_depth.py:88 loop, sharded).
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/ethcnn.h"
+#include "fc1_tc.h"
+#include "kernels.h"
+#include "model.h"
+#include "tf_bundle.h"
+
+namespace ethcnn {
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t e__ = (expr);                                                                            \
+    if (e__ != cudaSuccess)                                                                              \
+      return fail(ETHCNN_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));                   \
+  } while (0)
+
+struct DeviceModel {
+  float* conv = nullptr;
+  float* w1 = nullptr;
+  float* b1 = nullptr;
+  __half* w1_hi = nullptr;
+  __half* w1_lo = nullptr;
+  float* heads = nullptr;  // one allocation holding w2/w2q/b2/w3/w3q/b3 of the three heads
+  HeadWeights hw[3];
+  int feat_exp = 0, w_exp = 0;
+  Fc1TcWeights tc;         // tensor maps over w1_hi / w1_lo
+};
+
+struct ProfEvent {
+  int stage;
+  cudaEvent_t a, b;
+};
+
+struct DeviceCtx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+  std::map<std::string, DeviceModel> models;
+  // scratch for the device path
+  size_t chunk_ctus = 0;
+  __half* feat_hi = nullptr;
+  __half* feat_lo = nullptr;
+  float* fc1 = nullptr;
+  unsigned* flags = nullptr;
+  size_t flags_cap = 0;
+  cudaEvent_t ev_last = nullptr;  // end of the previous device call (scratch reuse across streams)
+  // staging for the host path
+  static constexpr int kSlabs = 2;
+  uint8_t* d_slab[kSlabs] = {nullptr, nullptr};
+  float* d_prob[kSlabs] = {nullptr, nullptr};
+  uint8_t* h_stage[kSlabs] = {nullptr, nullptr};
+  float* h_prob[kSlabs] = {nullptr, nullptr};
+  size_t slab_bytes = 0, slab_prob_floats = 0, stage_bytes = 0, hprob_floats = 0;
+  cudaEvent_t ev_h2d[kSlabs] = {nullptr, nullptr}, ev_comp[kSlabs] = {nullptr, nullptr}, ev_d2h[kSlabs] = {nullptr, nullptr};
+  // profiling
+  bool profiling = false;
+  std::vector<ProfEvent> prof;
+  double prof_ms[ETHCNN_N_STAGES] = {0, 0, 0, 0};
+  int64_t prof_launches[ETHCNN_N_STAGES] = {0, 0, 0, 0};
+  int last_used_tma = 0;
+  int last_feat_exp = 0;
+};
+
+}  // namespace
+}  // namespace ethcnn
+
+using namespace ethcnn;
+
+struct ethcnn_handle {
+  int mode = ETHCNN_MODE_AI;
+  std::string model_dir;
+  float t1 = 0.5f, t2 = 0.5f;
+  std::vector<std::unique_ptr<DeviceCtx>> devs;
+  std::mutex mu;
+  std::atomic<int64_t> launches{0};
+  int fc1_path = 1;
+  size_t chunk_ctus = 148 * 128;
+};
+
+namespace ethcnn {
+namespace {
+
+// ----------------------------------------------------------------------------------------------
+// Thr_info.txt: first line split on single spaces, tokens [1] and [3] (net_CNN.py:38-45).
+int read_thresholds(const std::string& path, float* t1, float* t2) {
+  FILE* f = fopen(path.c_str(), "r");
+  if (!f) return fail(ETHCNN_E_IO, "cannot open " + path);
+  char line[4096];
+  if (!fgets(line, sizeof(line), f)) {
+    fclose(f);
+    return fail(ETHCNN_E_FORMAT, path + ": empty");
+  }
+  fclose(f);
+  std::vector<std::string> tok;  // python str.split(' '): consecutive spaces give empty tokens
+  std::string cur;
+  for (const char* p = line; *p; ++p) {
+    if (*p == ' ') {
+      tok.push_back(cur);
+      cur.clear();
+    } else {
+      cur.push_back(*p);
+    }
+  }
+  tok.push_back(cur);
+  if (tok.size() < 4) return fail(ETHCNN_E_FORMAT, path + ": fewer than 4 tokens");
+  auto to_float = [](const std::string& s, float* out) {
+    char* end = nullptr;
+    const double v = strtod(s.c_str(), &end);
+    if (end == s.c_str()) return false;
+    while (*end == '\n' || *end == '\r' || *end == '\t') ++end;  // python float() strips whitespace
+    if (*end) return false;
+    *out = float(v);
+    return true;
+  };
+  if (!to_float(tok[1], t1) || !to_float(tok[3], t2)) return fail(ETHCNN_E_FORMAT, path + ": tokens [1]/[3] are not numbers");
+  return ETHCNN_OK;
+}
+
+// Model selection by QP range (video_to_cu_depth.py:126-133) / the single LDP CNN checkpoint
+// (resi_to_cu_depth_LDP.py:158-159).
+std::string model_prefix(int mode, int qp) {
+  if (mode == ETHCNN_MODE_LDP) return "model_LDP_2000000_qp22~37.dat";
+  if (qp < 25) return "model_2000000_qp20~25.dat";
+  if (qp < 30) return "model_2000000_qp25~30.dat";
+  if (qp < 35) return "model_2000000_qp30~35.dat";
+  return "model_2000000_qp35~40.dat";
+}
+
+float scaled_qp(int mode, int qp) {
+  if (mode == ETHCNN_MODE_LDP) return (float(qp) / 51.0f) * 0.18f;  // net_CTU64.py:103
+  return float(qp) * float(1.0 / 51.0);                             // net_CNN.py:106 (scalar_mul(1/51.0, qp))
+}
+
+template <class T>
+int upload(T** dst, const void* src, size_t bytes) {
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(dst), bytes));
+  CUDA_TRY(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+  return ETHCNN_OK;
+}
+
+void free_model(DeviceModel& m) {
+  cudaFree(m.conv), cudaFree(m.w1), cudaFree(m.b1), cudaFree(m.w1_hi), cudaFree(m.w1_lo), cudaFree(m.heads);
+  m = DeviceModel();
+}
+
+int get_model(ethcnn_handle* h, DeviceCtx& c, int qp, DeviceModel** out) {
+  const std::string prefix = model_prefix(h->mode, qp);
+  auto it = c.models.find(prefix);
+  if (it != c.models.end()) {
+    *out = &it->second;
+    return ETHCNN_OK;
+  }
+  std::map<std::string, BundleTensor> tensors;
+  std::string err;
+  const std::string path = h->model_dir.empty() ? prefix : h->model_dir + "/" + prefix;
+  if (!read_tf_bundle(path, &tensors, &err)) {
+    const bool io = err.find("cannot open") != std::string::npos;
+    return fail(io ? ETHCNN_E_IO : ETHCNN_E_FORMAT, err);
+  }
+  PackedModel pm;
+  if (!pack_model(tensors, h->mode == ETHCNN_MODE_LDP ? 10.0f : 1.0f, &pm, &err)) return fail(ETHCNN_E_FORMAT, path + ": " + err);
+  DeviceModel m;
+  int rc;
+  if ((rc = upload(&m.conv, pm.conv.data(), pm.conv.size() * 4))) return rc;
+  if ((rc = upload(&m.w1, pm.w1.data(), pm.w1.size() * 4))) return rc;
+  if ((rc = upload(&m.b1, pm.b1.data(), pm.b1.size() * 4))) return rc;
+  if ((rc = upload(&m.w1_hi, pm.w1_hi.data(), pm.w1_hi.size() * 2))) return rc;
+  if ((rc = upload(&m.w1_lo, pm.w1_lo.data(), pm.w1_lo.size() * 2))) return rc;
+  std::vector<float> hb;
+  size_t off[3][6];
+  for (int k = 0; k < 3; ++k) {
+    const std::vector<float>* parts[6] = {&pm.w2[k], &pm.w2q[k], &pm.b2[k], &pm.w3[k], &pm.w3q[k], &pm.b3[k]};
+    for (int j = 0; j < 6; ++j) {
+      while (hb.size() % 4) hb.push_back(0.f);
+      off[k][j] = hb.size();
+      hb.insert(hb.end(), parts[j]->begin(), parts[j]->end());
+    }
+  }
+  if ((rc = upload(&m.heads, hb.data(), hb.size() * 4))) return rc;
+  for (int k = 0; k < 3; ++k) {
+    m.hw[k].w2 = m.heads + off[k][0], m.hw[k].w2q = m.heads + off[k][1], m.hw[k].b2 = m.heads + off[k][2];
+    m.hw[k].w3 = m.heads + off[k][3], m.hw[k].w3q = m.heads + off[k][4], m.hw[k].b3 = m.heads + off[k][5];
+  }
+  m.feat_exp = pm.feat_exp;
+  m.w_exp = pm.w_exp;
+  const char* terr = nullptr;
+  if (!fc1_tc_prepare_weights(m.w1_hi, m.w1_lo, &m.tc, &terr)) return fail(ETHCNN_E_CUDA, std::string("FC1 weight tensor map: ") + terr);
+  auto ins = c.models.emplace(prefix, m);
+  *out = &ins.first->second;
+  return ETHCNN_OK;
+}
+
+int ensure_scratch(ethcnn_handle* h, DeviceCtx& c, size_t flags_needed) {
+  if (c.chunk_ctus != h->chunk_ctus || !c.feat_hi) {
+    cudaFree(c.feat_hi), cudaFree(c.feat_lo), cudaFree(c.fc1);
+    c.feat_hi = c.feat_lo = nullptr, c.fc1 = nullptr;
+    c.chunk_ctus = h->chunk_ctus;
+    // rows are padded to a multiple of 128 so the FC1 tile loads never leave the allocation
+    const size_t rows = (c.chunk_ctus + 127) / 128 * 128;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c.feat_hi), rows * kFeat * 2));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c.feat_lo), rows * kFeat * 2));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c.fc1), rows * kFc1 * 4));
+    CUDA_TRY(cudaMemset(c.feat_hi, 0, rows * kFeat * 2));
+    CUDA_TRY(cudaMemset(c.feat_lo, 0, rows * kFeat * 2));
+  }
+  if (flags_needed > c.flags_cap) {
+    cudaFree(c.flags);
+    c.flags = nullptr;
+    c.flags_cap = flags_needed * 2 + 64;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c.flags), c.flags_cap * sizeof(unsigned)));
+  }
+  return ETHCNN_OK;
+}
+
+struct StageTimer {
+  DeviceCtx& c;
+  cudaStream_t s;
+  int stage;
+  ProfEvent ev{};
+  bool on;
+  StageTimer(DeviceCtx& ctx, cudaStream_t stream, int st) : c(ctx), s(stream), stage(st), on(ctx.profiling) {
+    if (on) {
+      ev.stage = st;
+      cudaEventCreate(&ev.a);
+      cudaEventCreate(&ev.b);
+      cudaEventRecord(ev.a, s);
+    }
+  }
+  ~StageTimer() {
+    if (on) {
+      cudaEventRecord(ev.b, s);
+      c.prof.push_back(ev);
+    }
+  }
+};
+
+// The device-resident forward pass: everything is enqueued on `stream`, nothing is synchronised.
+// fc1_out != nullptr selects the LDP FC1 tap (conv + FC1 only, written to fc1_out [n][448]).
+int run_device(ethcnn_handle* h, DeviceCtx& c, const uint8_t* d_y, int width, int height, size_t pitch, size_t frame_stride,
+               int n_frames, int qp, float* d_out, float* fc1_out, cudaStream_t stream) {
+  if (width <= 0 || height <= 0 || n_frames < 0 || pitch < size_t(width)) return fail(ETHCNN_E_ARG, "bad frame geometry");
+  if (n_frames == 0) return ETHCNN_OK;
+  CUDA_TRY(cudaSetDevice(c.device));
+  DeviceModel* m = nullptr;
+  int rc = get_model(h, c, qp, &m);
+  if (rc) return rc;
+  const int ctu_cols = (width + kCtu - 1) / kCtu, ctu_rows = (height + kCtu - 1) / kCtu;
+  const int ctus_per_frame = ctu_cols * ctu_rows;
+  const int chunks_per_frame = (ctus_per_frame + kSubBatch - 1) / kSubBatch;
+  const long long total = (long long)n_frames * ctus_per_frame;
+  if (total > 0x7fffffffLL / 32) return fail(ETHCNN_E_ARG, "too many CTUs in one call; split the sequence");
+  if ((rc = ensure_scratch(h, c, size_t(n_frames) * chunks_per_frame))) return rc;
+  if (c.ev_last) CUDA_TRY(cudaStreamWaitEvent(stream, c.ev_last, 0));
+
+  CUtensorMap tmap;
+  const char* terr = nullptr;
+  const bool use_tma = make_luma_tensor_map(&tmap, d_y, width, height, n_frames, pitch, frame_stride, &terr);
+  c.last_used_tma = use_tma ? 1 : 0;
+  const bool gated = (h->mode == ETHCNN_MODE_AI) && fc1_out == nullptr;
+  if (gated) CUDA_TRY(cudaMemsetAsync(c.flags, 0, size_t(n_frames) * chunks_per_frame * sizeof(unsigned), stream));
+
+  const float in_scale = (h->mode == ETHCNN_MODE_LDP) ? (10.0f / 255.0f) : (1.0f / 255.0f);
+  for (long long begin = 0; begin < total; begin += (long long)c.chunk_ctus) {
+    const int n = int(std::min<long long>(c.chunk_ctus, total - begin));
+    ConvLaunch cl{};
+    cl.convw = m->conv;
+    cl.feat_hi = c.feat_hi, cl.feat_lo = c.feat_lo;
+    cl.n_ctus = n, cl.ctu_begin = int(begin), cl.ctus_per_row = ctu_cols, cl.ctus_per_frame = ctus_per_frame;
+    cl.cst[0] = in_scale / 256.0f, cl.cst[1] = in_scale / 1024.0f, cl.cst[2] = in_scale / 4096.0f;
+    cl.feat_scale = std::ldexp(1.0f, m->feat_exp);
+    c.last_feat_exp = m->feat_exp;
+    cl.luma = d_y, cl.pitch = pitch, cl.frame_stride = frame_stride, cl.width = width, cl.height = height;
+    {
+      StageTimer t(c, stream, ETHCNN_STAGE_CONV);
+      CUDA_TRY(launch_conv_features(use_tma ? &tmap : nullptr, cl, c.sm_count, stream));
+      ++h->launches;
+    }
+    float* fc1_dst = fc1_out ? fc1_out + size_t(begin) * kFc1 : c.fc1;
+    {
+      StageTimer t(c, stream, ETHCNN_STAGE_FC1);
+      if (h->fc1_path == 1) {
+        CUDA_TRY(launch_fc1_tc(c.feat_hi, c.feat_lo, m->tc, m->b1, std::ldexp(1.0f, -(m->feat_exp + m->w_exp)), fc1_dst, n,
+                               c.sm_count, stream));
+      } else {
+        CUDA_TRY(launch_fc1_simt(c.feat_hi, c.feat_lo, std::ldexp(1.0f, -m->feat_exp), m->w1, m->b1, fc1_dst, n, stream));
+      }
+      ++h->launches;
+    }
+    if (fc1_out) continue;
+    HeadsLaunch hl{};
+    hl.fc1 = c.fc1;
+    for (int k = 0; k < 3; ++k) hl.head[k] = m->hw[k];
+    hl.q = scaled_qp(h->mode, qp);
+    hl.prob = d_out;
+    hl.flags = gated ? c.flags : nullptr;
+    hl.t1 = h->t1, hl.t2 = h->t2;
+    hl.n_ctus = n, hl.ctu_begin = int(begin), hl.ctus_per_frame = ctus_per_frame, hl.chunks_per_frame = chunks_per_frame;
+    {
+      StageTimer t(c, stream, ETHCNN_STAGE_HEADS);
+      CUDA_TRY(launch_heads(hl, stream));
+      ++h->launches;
+    }
+  }
+  if (gated) {
+    StageTimer t(c, stream, ETHCNN_STAGE_GATE);
+    CUDA_TRY(launch_gate(d_out, c.flags, h->t2, total, ctus_per_frame, chunks_per_frame, stream));
+    ++h->launches;
+  }
+  if (!c.ev_last) CUDA_TRY(cudaEventCreateWithFlags(&c.ev_last, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventRecord(c.ev_last, stream));
+  return ETHCNN_OK;
+}
+
+bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+void parallel_copy_frames(uint8_t* dst, const uint8_t* src, size_t frame_bytes, size_t src_stride, int n_frames) {
+  const size_t total = frame_bytes * size_t(n_frames);
+  int nt = int(std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 8));
+  if (total < (size_t(4) << 20)) nt = 1;
+  auto work = [&](int t) {
+    // split by bytes so a single huge frame is still shared between threads
+    const size_t lo = total * t / nt, hi = total * (t + 1) / nt;
+    size_t pos = lo;
+    while (pos < hi) {
+      const size_t f = pos / frame_bytes, o = pos - f * frame_bytes;
+      const size_t len = std::min(frame_bytes - o, hi - pos);
+      memcpy(dst + pos, src + f * src_stride + o, len);
+      pos += len;
+    }
+  };
+  if (nt == 1) {
+    work(0);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto& x : th) x.join();
+}
+
+int ensure_staging(DeviceCtx& c, size_t slab_bytes, size_t slab_prob_floats, bool need_stage, bool need_hprob) {
+  if (slab_bytes > c.slab_bytes) {
+    for (int i = 0; i < DeviceCtx::kSlabs; ++i) {
+      cudaFree(c.d_slab[i]);
+      c.d_slab[i] = nullptr;
+      CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c.d_slab[i]), slab_bytes));
+    }
+    c.slab_bytes = slab_bytes;
+  }
+  if (slab_prob_floats > c.slab_prob_floats) {
+    for (int i = 0; i < DeviceCtx::kSlabs; ++i) {
+      cudaFree(c.d_prob[i]);
+      c.d_prob[i] = nullptr;
+      CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c.d_prob[i]), slab_prob_floats * 4));
+    }
+    c.slab_prob_floats = slab_prob_floats;
+  }
+  if (need_stage && slab_bytes > c.stage_bytes) {
+    for (int i = 0; i < DeviceCtx::kSlabs; ++i) {
+      cudaFreeHost(c.h_stage[i]);
+      c.h_stage[i] = nullptr;
+      CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&c.h_stage[i]), slab_bytes));
+    }
+    c.stage_bytes = slab_bytes;
+  }
+  if (need_hprob && slab_prob_floats > c.hprob_floats) {
+    for (int i = 0; i < DeviceCtx::kSlabs; ++i) {
+      cudaFreeHost(c.h_prob[i]);
+      c.h_prob[i] = nullptr;
+      CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&c.h_prob[i]), slab_prob_floats * 4));
+    }
+    c.hprob_floats = slab_prob_floats;
+  }
+  for (int i = 0; i < DeviceCtx::kSlabs; ++i) {
+    if (!c.ev_h2d[i]) CUDA_TRY(cudaEventCreateWithFlags(&c.ev_h2d[i], cudaEventDisableTiming));
+    if (!c.ev_comp[i]) CUDA_TRY(cudaEventCreateWithFlags(&c.ev_comp[i], cudaEventDisableTiming));
+    if (!c.ev_d2h[i]) CUDA_TRY(cudaEventCreateWithFlags(&c.ev_d2h[i], cudaEventDisableTiming));
+  }
+  return ETHCNN_OK;
+}
+
+// Host-input pipeline on ONE device for frames [0, n_frames) at y / out (already offset by the caller).
+// per_ctu_out = 21 (probabilities) or 448 (FC1 tap).
+int run_host_pipeline(ethcnn_handle* h, DeviceCtx& c, const uint8_t* y, int width, int height, size_t frame_stride,
+                      int n_frames, int qp, float* out, bool fc1_tap) {
+  if (n_frames <= 0) return ETHCNN_OK;
+  CUDA_TRY(cudaSetDevice(c.device));
+  const int per_ctu = fc1_tap ? kFc1 : kProbs;
+  const size_t luma_bytes = size_t(width) * height;
+  const size_t pitch = (size_t(width) + 15) / 16 * 16;
+  const size_t dev_frame = pitch * height;  // multiple of 16
+  const int ctus_per_frame = ((width + kCtu - 1) / kCtu) * ((height + kCtu - 1) / kCtu);
+  const size_t target = size_t(48) << 20;
+  int slab_frames = int(std::max<size_t>(1, std::min<size_t>(size_t(n_frames), target / dev_frame)));
+  // at least two slabs when there is more than one frame, so the copies overlap the kernels
+  if (n_frames > 1 && slab_frames > (n_frames + 1) / 2) slab_frames = (n_frames + 1) / 2;
+  const bool src_pinned = is_pinned(y);
+  const bool dst_pinned = is_pinned(out);
+  int rc = ensure_staging(c, dev_frame * slab_frames, size_t(slab_frames) * ctus_per_frame * per_ctu, !src_pinned, !dst_pinned);
+  if (rc) return rc;
+
+  struct Pending {
+    int slab = -1, f0 = 0, nf = 0;
+  } pend[DeviceCtx::kSlabs];
+  auto drain = [&](int b) -> int {  // finish the D2H of buffer b and hand the rows to the caller
+    if (pend[b].slab < 0) return ETHCNN_OK;
+    CUDA_TRY(cudaEventSynchronize(c.ev_d2h[b]));
+    if (!dst_pinned)
+      memcpy(out + size_t(pend[b].f0) * ctus_per_frame * per_ctu, c.h_prob[b], size_t(pend[b].nf) * ctus_per_frame * per_ctu * 4);
+    pend[b].slab = -1;
+    return ETHCNN_OK;
+  };
+
+  int slab_idx = 0;
+  for (int f0 = 0; f0 < n_frames; f0 += slab_frames, ++slab_idx) {
+    const int nf = std::min(slab_frames, n_frames - f0);
+    const int b = slab_idx % DeviceCtx::kSlabs;
+    if ((rc = drain(b))) return rc;  // also guarantees buffer b (device slab, staging, prob) is free
+    const uint8_t* src = y + size_t(f0) * frame_stride;
+    size_t src_stride = frame_stride;
+    if (!src_pinned) {
+      parallel_copy_frames(c.h_stage[b], src, luma_bytes, frame_stride, nf);
+      src = c.h_stage[b];
+      src_stride = luma_bytes;
+    }
+    if (pitch == size_t(width)) {
+      CUDA_TRY(cudaMemcpy2DAsync(c.d_slab[b], dev_frame, src, src_stride, luma_bytes, nf, cudaMemcpyHostToDevice, c.s_h2d));
+    } else {
+      for (int f = 0; f < nf; ++f)
+        CUDA_TRY(cudaMemcpy2DAsync(c.d_slab[b] + size_t(f) * dev_frame, pitch, src + size_t(f) * src_stride, width, width, height,
+                                   cudaMemcpyHostToDevice, c.s_h2d));
+    }
+    CUDA_TRY(cudaEventRecord(c.ev_h2d[b], c.s_h2d));
+    CUDA_TRY(cudaStreamWaitEvent(c.s_compute, c.ev_h2d[b], 0));
+    rc = run_device(h, c, c.d_slab[b], width, height, pitch, dev_frame, nf, qp, fc1_tap ? nullptr : c.d_prob[b],
+                    fc1_tap ? c.d_prob[b] : nullptr, c.s_compute);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(c.ev_comp[b], c.s_compute));
+    CUDA_TRY(cudaStreamWaitEvent(c.s_d2h, c.ev_comp[b], 0));
+    const size_t nfl = size_t(nf) * ctus_per_frame * per_ctu;
+    float* dst = dst_pinned ? out + size_t(f0) * ctus_per_frame * per_ctu : c.h_prob[b];
+    CUDA_TRY(cudaMemcpyAsync(dst, c.d_prob[b], nfl * 4, cudaMemcpyDeviceToHost, c.s_d2h));
+    CUDA_TRY(cudaEventRecord(c.ev_d2h[b], c.s_d2h));
+    // the next H2D into this device slab must not start before these kernels have consumed it
+    CUDA_TRY(cudaStreamWaitEvent(c.s_h2d, c.ev_comp[b], 0));
+    pend[b].slab = slab_idx, pend[b].f0 = f0, pend[b].nf = nf;
+  }
+  for (int b = 0; b < DeviceCtx::kSlabs; ++b)
+    if ((rc = drain(b))) return rc;
+  return ETHCNN_OK;
+}
+
+// Contiguous frame ranges per device: the first (n % G) devices take one extra frame.
+void frame_range(int n_frames, int n_dev, int r, int* f0, int* nf) {
+  const int base = n_frames / n_dev, rem = n_frames % n_dev;
+  *f0 = r * base + std::min(r, rem);
+  *nf = base + (r < rem ? 1 : 0);
+}
+
+int run_host_all_devices(ethcnn_handle* h, const uint8_t* y, int width, int height, size_t frame_stride, int n_frames, int qp,
+                         float* out, bool fc1_tap) {
+  const int per_ctu = fc1_tap ? kFc1 : kProbs;
+  const size_t ctus_per_frame = size_t((width + kCtu - 1) / kCtu) * ((height + kCtu - 1) / kCtu);
+  const int nd = int(h->devs.size());
+  if (nd == 1 || n_frames < 2) return run_host_pipeline(h, *h->devs[0], y, width, height, frame_stride, n_frames, qp, out, fc1_tap);
+  std::vector<int> rcs(nd, 0);
+  std::vector<std::string> errs(nd);
+  std::vector<std::thread> th;
+  for (int r = 0; r < nd; ++r) {
+    th.emplace_back([&, r]() {
+      int f0, nf;
+      frame_range(n_frames, nd, r, &f0, &nf);
+      rcs[r] = run_host_pipeline(h, *h->devs[r], y + size_t(f0) * frame_stride, width, height, frame_stride, nf, qp,
+                                 out + size_t(f0) * ctus_per_frame * per_ctu, fc1_tap);
+      if (rcs[r]) errs[r] = g_last_error;
+    });
+  }
+  for (auto& t : th) t.join();
+  for (int r = 0; r < nd; ++r)
+    if (rcs[r]) return fail(rcs[r], "device " + std::to_string(h->devs[r]->device) + ": " + errs[r]);
+  return ETHCNN_OK;
+}
+
+int open_device(ethcnn_handle* h, int device) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return fail(ETHCNN_E_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  }
+  if (device < 0 || device >= count) return fail(ETHCNN_E_ARG, "CUDA device " + std::to_string(device) + " does not exist");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(ETHCNN_E_CUDA, std::string("device is ") + prop.name + " (sm_" + std::to_string(prop.major) +
+                                                        std::to_string(prop.minor) + "); this build targets sm_100a only");
+  std::unique_ptr<DeviceCtx> c(new DeviceCtx());
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+  CUDA_TRY(conv_features_configure());
+  CUDA_TRY(fc1_tc_configure());
+  h->devs.push_back(std::move(c));
+  return ETHCNN_OK;
+}
+
+void close_device(DeviceCtx& c) {
+  cudaSetDevice(c.device);
+  cudaDeviceSynchronize();
+  for (auto& kv : c.models) free_model(kv.second);
+  cudaFree(c.feat_hi), cudaFree(c.feat_lo), cudaFree(c.fc1), cudaFree(c.flags);
+  for (int i = 0; i < DeviceCtx::kSlabs; ++i) {
+    cudaFree(c.d_slab[i]), cudaFree(c.d_prob[i]), cudaFreeHost(c.h_stage[i]), cudaFreeHost(c.h_prob[i]);
+    if (c.ev_h2d[i]) cudaEventDestroy(c.ev_h2d[i]);
+    if (c.ev_comp[i]) cudaEventDestroy(c.ev_comp[i]);
+    if (c.ev_d2h[i]) cudaEventDestroy(c.ev_d2h[i]);
+  }
+  for (auto& e : c.prof) cudaEventDestroy(e.a), cudaEventDestroy(e.b);
+  if (c.ev_last) cudaEventDestroy(c.ev_last);
+  if (c.s_compute) cudaStreamDestroy(c.s_compute);
+  if (c.s_h2d) cudaStreamDestroy(c.s_h2d);
+  if (c.s_d2h) cudaStreamDestroy(c.s_d2h);
+}
+
+int create_common(const char* model_dir, const char* thr_path, int mode, const std::vector<int>& devices, ethcnn_handle** out) {
+  if (!out) return fail(ETHCNN_E_ARG, "out is NULL");
+  *out = nullptr;
+  if (mode != ETHCNN_MODE_AI && mode != ETHCNN_MODE_LDP) return fail(ETHCNN_E_ARG, "unknown mode");
+  std::unique_ptr<ethcnn_handle> h(new ethcnn_handle());
+  h->mode = mode;
+  h->model_dir = (model_dir && *model_dir) ? model_dir : ".";
+  if (const char* e = getenv("ETHCNN_FC1")) h->fc1_path = (strcmp(e, "simt") == 0) ? 0 : 1;
+  if (mode == ETHCNN_MODE_AI) {
+    const std::string tp = thr_path ? std::string(thr_path) : h->model_dir + "/Thr_info.txt";
+    int rc = read_thresholds(tp, &h->t1, &h->t2);
+    if (rc) return rc;
+  }
+  for (int d : devices) {
+    int rc = open_device(h.get(), d);
+    if (rc) {
+      for (auto& c : h->devs) close_device(*c);
+      return rc;
+    }
+  }
+  *out = h.release();
+  return ETHCNN_OK;
+}
+
+}  // namespace
+}  // namespace ethcnn
+
+// =================================================================================================
+extern "C" {
+
+int ethcnn_abi_version(void) { return ETHCNN_ABI_VERSION; }
+
+const char* ethcnn_last_error(void) { return g_last_error.c_str(); }
+
+int ethcnn_create(const char* model_dir, const char* thr_path, int mode, int n_gpus, ethcnn_handle** out) {
+  if (n_gpus < 1) return fail(ETHCNN_E_ARG, "n_gpus must be >= 1");
+  std::vector<int> devs;
+  for (int i = 0; i < n_gpus; ++i) devs.push_back(i);
+  return create_common(model_dir, thr_path, mode, devs, out);
+}
+
+int ethcnn_create_on_device(const char* model_dir, const char* thr_path, int mode, int device, ethcnn_handle** out) {
+  return create_common(model_dir, thr_path, mode, std::vector<int>{device}, out);
+}
+
+void ethcnn_destroy(ethcnn_handle* h) {
+  if (!h) return;
+  for (auto& c : h->devs) close_device(*c);
+  delete h;
+}
+
+int ethcnn_predict_luma_device(ethcnn_handle* h, const uint8_t* d_y, int width, int height, size_t pitch, size_t frame_stride,
+                               int n_frames, int qp, float* d_out, void* stream) {
+  if (!h || !d_y || !d_out) return fail(ETHCNN_E_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lock(h->mu);
+  return run_device(h, *h->devs[0], d_y, width, height, pitch, frame_stride, n_frames, qp, d_out, nullptr,
+                    static_cast<cudaStream_t>(stream));
+}
+
+int ethcnn_predict_luma(ethcnn_handle* h, const uint8_t* y, int width, int height, size_t frame_stride, int n_frames, int qp,
+                        float* out) {
+  if (!h || (!y && n_frames > 0) || (!out && n_frames > 0)) return fail(ETHCNN_E_ARG, "NULL argument");
+  if (width <= 0 || height <= 0 || n_frames < 0 || frame_stride < size_t(width) * height) return fail(ETHCNN_E_ARG, "bad frame geometry");
+  std::lock_guard<std::mutex> lock(h->mu);
+  return run_host_all_devices(h, y, width, height, frame_stride, n_frames, qp, out, false);
+}
+
+int ethcnn_export_fc1(ethcnn_handle* h, const uint8_t* y, int width, int height, size_t frame_stride, int n_frames, float* out) {
+  if (!h || (!y && n_frames > 0) || (!out && n_frames > 0)) return fail(ETHCNN_E_ARG, "NULL argument");
+  if (h->mode != ETHCNN_MODE_LDP) return fail(ETHCNN_E_ARG, "ethcnn_export_fc1 requires ETHCNN_MODE_LDP");
+  if (width <= 0 || height <= 0 || n_frames < 0 || frame_stride < size_t(width) * height) return fail(ETHCNN_E_ARG, "bad frame geometry");
+  std::lock_guard<std::mutex> lock(h->mu);
+  return run_host_all_devices(h, y, width, height, frame_stride, n_frames, 0, out, true);
+}
+
+int ethcnn_predict_yuv_file(ethcnn_handle* h, const char* yuv_path, int width, int height, int qp, const char* out_path) {
+  if (!h || !yuv_path || !out_path) return fail(ETHCNN_E_ARG, "NULL argument");
+  if (width <= 0 || height <= 0) return fail(ETHCNN_E_ARG, "bad frame geometry");
+  const int fd = open(yuv_path, O_RDONLY);
+  if (fd < 0) return fail(ETHCNN_E_IO, std::string("cannot open ") + yuv_path);
+  struct stat st;
+  if (fstat(fd, &st) != 0) {
+    close(fd);
+    return fail(ETHCNN_E_IO, std::string("cannot stat ") + yuv_path);
+  }
+  const size_t file_bytes = size_t(st.st_size);
+  const size_t frame_bytes = size_t(width) * height * 3 / 2;
+  if (frame_bytes == 0 || file_bytes % frame_bytes != 0) {  // video_to_cu_depth.py:137
+    close(fd);
+    return fail(ETHCNN_E_ARG, "file size is not a whole number of " + std::to_string(width) + "x" + std::to_string(height) +
+                                  " 4:2:0 frames (file_bytes % frame_bytes != 0)");
+  }
+  const size_t n_frames = file_bytes / frame_bytes;
+  if (n_frames > size_t(0x7fffffff)) {
+    close(fd);
+    return fail(ETHCNN_E_ARG, "too many frames");
+  }
+  const uint8_t* base = nullptr;
+  if (file_bytes) {
+    void* mp = mmap(nullptr, file_bytes, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (mp == MAP_FAILED) {
+      close(fd);
+      return fail(ETHCNN_E_IO, std::string("cannot map ") + yuv_path);
+    }
+    madvise(mp, file_bytes, MADV_SEQUENTIAL);
+    base = static_cast<const uint8_t*>(mp);
+  }
+  const size_t ctus = size_t((width + kCtu - 1) / kCtu) * ((height + kCtu - 1) / kCtu);
+  std::vector<float> prob(n_frames * ctus * kProbs);
+  int rc;
+  {
+    std::lock_guard<std::mutex> lock(h->mu);
+    rc = run_host_all_devices(h, base, width, height, frame_bytes, int(n_frames), qp, prob.data(), false);
+  }
+  if (base) munmap(const_cast<uint8_t*>(base), file_bytes);
+  close(fd);
+  if (rc) return rc;
+  // single write at the end (video_to_cu_depth.py:114-116), via a temporary so failures leave no partial file
+  const std::string tmp = std::string(out_path) + ".tmp." + std::to_string(getpid());
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) return fail(ETHCNN_E_IO, "cannot create " + tmp);
+  const size_t wrote = prob.empty() ? 0 : fwrite(prob.data(), sizeof(float), prob.size(), f);
+  const bool ok = (wrote == prob.size()) && (fclose(f) == 0);
+  if (!ok) {
+    remove(tmp.c_str());
+    return fail(ETHCNN_E_IO, "short write on " + tmp);
+  }
+  if (rename(tmp.c_str(), out_path) != 0) {
+    remove(tmp.c_str());
+    return fail(ETHCNN_E_IO, std::string("cannot rename onto ") + out_path);
+  }
+  return ETHCNN_OK;
+}
+
+int ethcnn_decisions(ethcnn_handle* h, const float* prob, size_t n_ctus, const float thr6[6], uint8_t* decision) {
+  if (!h || !thr6 || ((!prob || !decision) && n_ctus)) return fail(ETHCNN_E_ARG, "NULL argument");
+  if (n_ctus == 0) return ETHCNN_OK;
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceCtx& c = *h->devs[0];
+  CUDA_TRY(cudaSetDevice(c.device));
+  const size_t n = n_ctus * kProbs;
+  float *d_p = nullptr, *d_t = nullptr;
+  unsigned char* d_d = nullptr;
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_p), n * 4));
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_t), 6 * 4));
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_d), n));
+  cudaError_t e = cudaMemcpyAsync(d_p, prob, n * 4, cudaMemcpyHostToDevice, c.s_compute);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_t, thr6, 24, cudaMemcpyHostToDevice, c.s_compute);
+  if (e == cudaSuccess) e = launch_decisions(d_p, d_d, (long long)n, d_t, c.s_compute);
+  ++h->launches;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(decision, d_d, n, cudaMemcpyDeviceToHost, c.s_compute);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c.s_compute);
+  cudaFree(d_p), cudaFree(d_t), cudaFree(d_d);
+  if (e != cudaSuccess) return fail(ETHCNN_E_CUDA, std::string("decisions: ") + cudaGetErrorString(e));
+  return ETHCNN_OK;
+}
+
+int ethcnn_query(ethcnn_handle* h, int what, int64_t* value) {
+  if (!h || !value) return fail(ETHCNN_E_ARG, "NULL argument");
+  switch (what) {
+    case ETHCNN_Q_KERNEL_LAUNCHES: *value = h->launches.load(); break;
+    case ETHCNN_Q_N_DEVICES: *value = int64_t(h->devs.size()); break;
+    case ETHCNN_Q_FC1_PATH: *value = h->fc1_path; break;
+    case ETHCNN_Q_TMA_LOADER_USED: *value = h->devs[0]->last_used_tma; break;
+    case ETHCNN_Q_SM_COUNT: *value = h->devs[0]->sm_count; break;
+    default: return fail(ETHCNN_E_ARG, "unknown query");
+  }
+  return ETHCNN_OK;
+}
+
+int ethcnn_set_option(ethcnn_handle* h, int option, int64_t value) {
+  if (!h) return fail(ETHCNN_E_ARG, "NULL handle");
+  std::lock_guard<std::mutex> lock(h->mu);
+  switch (option) {
+    case ETHCNN_OPT_FC1_PATH:
+      if (value != 0 && value != 1) return fail(ETHCNN_E_ARG, "FC1 path must be 0 or 1");
+      h->fc1_path = int(value);
+      break;
+    case ETHCNN_OPT_CHUNK_CTUS:
+      if (value < 1 || value > (1 << 22)) return fail(ETHCNN_E_ARG, "chunk size out of range");
+      h->chunk_ctus = size_t(value);
+      break;
+    default: return fail(ETHCNN_E_ARG, "unknown option");
+  }
+  return ETHCNN_OK;
+}
+
+int ethcnn_profile_enable(ethcnn_handle* h, int on) {
+  if (!h) return fail(ETHCNN_E_ARG, "NULL handle");
+  std::lock_guard<std::mutex> lock(h->mu);
+  for (auto& c : h->devs) c->profiling = on != 0;
+  return ETHCNN_OK;
+}
+
+int ethcnn_profile_read(ethcnn_handle* h, int stage, double* ms_total, int64_t* launches, int reset) {
+  if (!h || stage < 0 || stage >= ETHCNN_N_STAGES) return fail(ETHCNN_E_ARG, "bad stage");
+  std::lock_guard<std::mutex> lock(h->mu);
+  double ms = 0;
+  int64_t n = 0;
+  for (auto& cp : h->devs) {
+    DeviceCtx& c = *cp;
+    CUDA_TRY(cudaSetDevice(c.device));
+    for (auto& e : c.prof) {  // fold finished event pairs into the per-stage totals
+      CUDA_TRY(cudaEventSynchronize(e.b));
+      float t = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&t, e.a, e.b));
+      c.prof_ms[e.stage] += t;
+      c.prof_launches[e.stage] += 1;
+      cudaEventDestroy(e.a), cudaEventDestroy(e.b);
+    }
+    c.prof.clear();
+    ms += c.prof_ms[stage];
+    n += c.prof_launches[stage];
+    if (reset) c.prof_ms[stage] = 0, c.prof_launches[stage] = 0;
+  }
+  if (ms_total) *ms_total = ms;
+  if (launches) *launches = n;
+  return ETHCNN_OK;
+}
+
+int ethcnn_debug_pack_model(const char* ckpt_prefix, float input_bound, float* conv, float* w1, float* b1, uint16_t* w1_hi,
+                            uint16_t* w1_lo, int exps[2], float* feat_bound) {
+  if (!ckpt_prefix) return fail(ETHCNN_E_ARG, "NULL argument");
+  std::map<std::string, BundleTensor> tensors;
+  std::string err;
+  if (!read_tf_bundle(ckpt_prefix, &tensors, &err))
+    return fail(err.find("cannot open") != std::string::npos ? ETHCNN_E_IO : ETHCNN_E_FORMAT, err);
+  PackedModel pm;
+  if (!pack_model(tensors, input_bound, &pm, &err)) return fail(ETHCNN_E_FORMAT, err);
+  if (conv) memcpy(conv, pm.conv.data(), pm.conv.size() * 4);
+  if (w1) memcpy(w1, pm.w1.data(), pm.w1.size() * 4);
+  if (b1) memcpy(b1, pm.b1.data(), pm.b1.size() * 4);
+  if (w1_hi) memcpy(w1_hi, pm.w1_hi.data(), pm.w1_hi.size() * 2);
+  if (w1_lo) memcpy(w1_lo, pm.w1_lo.data(), pm.w1_lo.size() * 2);
+  if (exps) exps[0] = pm.feat_exp, exps[1] = pm.w_exp;
+  if (feat_bound) *feat_bound = pm.feat_bound;
+  return ETHCNN_OK;
+}
+
+int ethcnn_debug_read_thresholds(const char* thr_path, float thr[2]) {
+  if (!thr_path || !thr) return fail(ETHCNN_E_ARG, "NULL argument");
+  return read_thresholds(thr_path, &thr[0], &thr[1]);
+}
+
+uint16_t ethcnn_debug_f32_to_f16(float v) { return f32_to_f16_bits(v); }
+
+int ethcnn_debug_read_scratch(ethcnn_handle* h, int what, size_t n_ctus, float* out) {
+  if (!h || !out) return fail(ETHCNN_E_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceCtx& c = *h->devs[0];
+  if (!c.feat_hi || n_ctus > c.chunk_ctus) return fail(ETHCNN_E_ARG, "no scratch of that size");
+  CUDA_TRY(cudaSetDevice(c.device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (what == 1) {
+    CUDA_TRY(cudaMemcpy(out, c.fc1, n_ctus * kFc1 * 4, cudaMemcpyDeviceToHost));
+    return ETHCNN_OK;
+  }
+  if (what != 0) return fail(ETHCNN_E_ARG, "unknown scratch id");
+  std::vector<uint16_t> hi(n_ctus * kFeat), lo(n_ctus * kFeat);
+  CUDA_TRY(cudaMemcpy(hi.data(), c.feat_hi, hi.size() * 2, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(lo.data(), c.feat_lo, lo.size() * 2, cudaMemcpyDeviceToHost));
+  const float inv = std::ldexp(1.0f, -c.last_feat_exp);
+  for (size_t i = 0; i < hi.size(); ++i) out[i] = (f16_bits_to_f32(hi[i]) + f16_bits_to_f32(lo[i])) * inv;
+  return ETHCNN_OK;
+}
+
+void* ethcnn_alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+    fail(ETHCNN_E_NOMEM, "cudaMallocHost failed");
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void ethcnn_free_pinned(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

@@ -1,0 +1,97 @@
+// Device-side stages of the ETH-CNN forward pass (sm_100a) and their host launchers.
+//   stage CONV  : 64x64 luma tiles (TMA) -> mean removal -> three conv branches -> 2688 features,
+//                 stored as scaled fp16 hi/lo pairs                      (net_CNN.py:105-150)
+//   stage FC1   : [n,2688] x [2688,448] + bias + leaky -> [n,448] fp32    (net_CNN.py:156,166,178)
+//                 tcgen05 (3-pass hi/lo split fp16, fp32 accumulate in TMEM) or SIMT fp32
+//   stage HEADS : FC2 + FC3 + sigmoid, raw probabilities + gate flags      (net_CNN.py:158-185)
+//   stage GATE  : per <=1024-CTU sub-batch gates                           (net_CNN.py:175,187)
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace ethcnn {
+
+constexpr int kCtu = 64;
+constexpr int kFeat = 2688;        // net_CNN.py:27
+constexpr int kFc1 = 448;          // 64 + 128 + 256
+constexpr int kProbs = 21;
+constexpr int kSubBatch = 1024;    // video_to_cu_depth.py:64
+
+// feature offsets inside the 2688-vector (net_CNN.py:150 concat order)
+constexpr int kOffC3S = 0, kOffC3M = 512, kOffC3L = 640, kOffC2S = 672, kOffC2M = 2208, kOffC2L = 2592;
+
+// conv weight block of one branch as laid out in shared memory (floats)
+constexpr int kW1Off = 0;        // [16 taps][16 co]
+constexpr int kB1Off = 256;      // [16]
+constexpr int kW2Off = 272;      // [4 patches][16 ci][24 co]
+constexpr int kB2Off = 1808;     // [24]
+constexpr int kW3Off = 1832;     // [4 quad lanes][24 ci][32 co] + 4 floats of padding per quad lane
+constexpr int kW3Stride = 772;
+constexpr int kB3Off = 4920;     // [32]
+constexpr int kConvBranchFloats = 4952;
+constexpr int kConvFloats = 3 * kConvBranchFloats;  // branch order S, M, L
+
+// conv-stage tiling
+constexpr int kGroupCtus = 8;     // CTUs per shared-memory tile group
+constexpr int kGroupTasks = 21;   // 16 S + 4 M + 1 L warp tasks per group
+constexpr int kConvStages = 4;
+constexpr int kConvComputeWarps = 11;  // 12 warps per CTA = 3 per SM sub-partition -> 168 registers per thread
+constexpr int kConvThreads = 32 * (1 + kConvComputeWarps);
+
+struct ConvLaunch {
+  const float* convw;        // device [kConvFloats]
+  __half* feat_hi;           // device [n_ctus][kFeat], value * feat_scale rounded to fp16
+  __half* feat_lo;           // device [n_ctus][kFeat], residual of the above
+  int n_ctus;                // CTUs in this launch
+  int ctu_begin;             // global index (frame-major raster) of the first CTU of this launch
+  int ctus_per_row;
+  int ctus_per_frame;
+  float cst[3];              // S, M, L: input_scale / (256 * pool^2)
+  float feat_scale;          // power of two
+  // plain-load tile loader (used when the TMA preconditions do not hold)
+  const uint8_t* luma;
+  size_t pitch, frame_stride;
+  int width, height;
+};
+
+struct HeadWeights {         // one head (64 / 32 / 16); all device pointers
+  const float* w2;           // [n1][n2]
+  const float* w2q;          // [n2]   the qp row of the FC2 matrix
+  const float* b2;           // [n2]
+  const float* w3;           // [n2][n3]
+  const float* w3q;          // [n3]
+  const float* b3;           // [n3]
+};
+
+struct HeadsLaunch {
+  const float* fc1;          // [n_ctus][448] after bias + leaky
+  HeadWeights head[3];
+  float q;                   // scaled qp
+  float* prob;               // [total][21], row of CTU i at prob + (ctu_begin + i) * 21
+  unsigned* flags;           // [n_frames * chunks_per_frame], bit0: any y64 > t1, bit1: any y32 > t2
+  float t1, t2;
+  int n_ctus, ctu_begin, ctus_per_frame, chunks_per_frame;
+};
+
+// CUtensorMap over the luma planes: dims (width, height, n_frames), box 64 x 64 x 1, zero OOB fill.
+bool make_luma_tensor_map(CUtensorMap* map, const uint8_t* d_y, int width, int height, int n_frames, size_t pitch,
+                          size_t frame_stride, const char** err);
+
+cudaError_t launch_conv_features(const CUtensorMap* tmap /* nullptr = plain loads */, const ConvLaunch& p, int sm_count,
+                                 cudaStream_t stream);
+cudaError_t conv_features_configure();  // one-off cudaFuncSetAttribute calls
+
+cudaError_t launch_fc1_simt(const __half* feat_hi, const __half* feat_lo, float inv_feat_scale, const float* w1 /*[2688][448]*/,
+                            const float* b1, float* fc1_out, int n_ctus, cudaStream_t stream);
+
+cudaError_t launch_heads(const HeadsLaunch& p, cudaStream_t stream);
+
+cudaError_t launch_gate(float* prob, const unsigned* flags, float t2, long long n_total, int ctus_per_frame,
+                        int chunks_per_frame, cudaStream_t stream);
+
+cudaError_t launch_decisions(const float* prob, unsigned char* dec, long long n_values, const float* thr6_dev,
+                             cudaStream_t stream);
+
+}  // namespace ethcnn

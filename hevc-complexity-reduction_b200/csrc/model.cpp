@@ -1,0 +1,179 @@
+#include "model.h"
+
+#include <cmath>
+#include <cstring>
+
+#include "kernels.h"
+
+namespace ethcnn {
+
+uint16_t f32_to_f16_bits(float f) {
+  uint32_t x;
+  memcpy(&x, &f, 4);
+  const uint32_t sign = (x >> 16) & 0x8000u;
+  const uint32_t em = x & 0x7fffffffu;
+  if (em >= 0x7f800000u) return uint16_t(sign | 0x7c00u | ((em > 0x7f800000u) ? 0x200u : 0));  // inf / nan
+  if (em >= 0x477ff000u) return uint16_t(sign | 0x7c00u);                                      // rounds to >= 65520 -> inf
+  if (em < 0x33000001u) return uint16_t(sign);                                                 // < 2^-25 -> 0
+  int exp = int(em >> 23) - 127;
+  uint32_t mant = (em & 0x7fffffu) | 0x800000u;
+  int shift;
+  uint32_t base;
+  if (exp >= -14) {  // normal half
+    shift = 13;
+    base = uint32_t(exp + 15) << 10;
+    mant &= 0x7fffffu;
+  } else {  // subnormal half: value = mant * 2^(exp-23), unit 2^-24
+    shift = 13 + (-14 - exp);
+    base = 0;
+  }
+  uint32_t q = mant >> shift;
+  const uint32_t rem = mant & ((1u << shift) - 1), halfway = 1u << (shift - 1);
+  if (rem > halfway || (rem == halfway && (q & 1))) ++q;
+  return uint16_t(sign | (base + q));  // a carry out of the mantissa correctly bumps the exponent
+}
+
+float f16_bits_to_f32(uint16_t h) {
+  const uint32_t sign = uint32_t(h & 0x8000u) << 16;
+  const uint32_t exp = (h >> 10) & 0x1f, mant = h & 0x3ffu;
+  float v;
+  if (exp == 0) {
+    v = std::ldexp(float(mant), -24);
+  } else if (exp == 31) {
+    v = mant ? NAN : INFINITY;
+  } else {
+    v = std::ldexp(float(mant | 0x400u), int(exp) - 25);
+  }
+  uint32_t bits;
+  memcpy(&bits, &v, 4);
+  bits |= sign;
+  memcpy(&v, &bits, 4);
+  return v;
+}
+
+namespace {
+
+std::string var_name(int i) { return i == 0 ? "Variable" : "Variable_" + std::to_string(i); }
+
+const BundleTensor* find(const std::map<std::string, BundleTensor>& t, const std::string& name,
+                         std::initializer_list<int64_t> shape, std::string* err) {
+  auto it = t.find(name);
+  if (it == t.end()) {
+    *err = "checkpoint lacks tensor " + name;
+    return nullptr;
+  }
+  if (it->second.shape != std::vector<int64_t>(shape)) {
+    *err = "tensor " + name + " has an unexpected shape";
+    return nullptr;
+  }
+  return &it->second;
+}
+
+}  // namespace
+
+bool pack_model(const std::map<std::string, BundleTensor>& t, float input_bound, PackedModel* out, std::string* err) {
+  out->conv.assign(kConvFloats, 0.f);
+  const int branch_base[3] = {12, 6, 0};  // S, M, L -> first Variable index (net_CNN.py:126-141)
+  float feat_bound = 0.f;
+  for (int br = 0; br < 3; ++br) {
+    const int v = branch_base[br];
+    const BundleTensor* w1 = find(t, var_name(v), {4, 4, 1, 16}, err);
+    const BundleTensor* b1 = find(t, var_name(v + 1), {16}, err);
+    const BundleTensor* w2 = find(t, var_name(v + 2), {2, 2, 16, 24}, err);
+    const BundleTensor* b2 = find(t, var_name(v + 3), {24}, err);
+    const BundleTensor* w3 = find(t, var_name(v + 4), {2, 2, 24, 32}, err);
+    const BundleTensor* b3 = find(t, var_name(v + 5), {32}, err);
+    if (!w1 || !b1 || !w2 || !b2 || !w3 || !b3) return false;
+    float* dst = out->conv.data() + br * kConvBranchFloats;
+    memcpy(dst + kW1Off, w1->data.data(), 256 * 4);   // [ky*4+kx][co]
+    memcpy(dst + kB1Off, b1->data.data(), 16 * 4);
+    memcpy(dst + kW2Off, w2->data.data(), 1536 * 4);  // [ky*2+kx][ci][co]
+    memcpy(dst + kB2Off, b2->data.data(), 24 * 4);
+    for (int d = 0; d < 4; ++d) memcpy(dst + kW3Off + d * kW3Stride, w3->data.data() + d * 768, 768 * 4);
+    memcpy(dst + kB3Off, b3->data.data(), 32 * 4);
+    // rigorous magnitude bounds (leaky never increases |.|)
+    double B1[16], B2[24], B3[32];
+    for (int co = 0; co < 16; ++co) {
+      double s = 0;
+      for (int k = 0; k < 16; ++k) s += std::fabs(w1->data[k * 16 + co]);
+      B1[co] = s * input_bound + std::fabs(b1->data[co]);
+    }
+    for (int co = 0; co < 24; ++co) {
+      double s = 0;
+      for (int k = 0; k < 64; ++k) s += std::fabs(w2->data[k * 24 + co]) * B1[k % 16];
+      B2[co] = s + std::fabs(b2->data[co]);
+      if (B2[co] > feat_bound) feat_bound = float(B2[co]);
+    }
+    for (int co = 0; co < 32; ++co) {
+      double s = 0;
+      for (int k = 0; k < 96; ++k) s += std::fabs(w3->data[k * 32 + co]) * B2[k % 24];
+      B3[co] = s + std::fabs(b3->data[co]);
+      if (B3[co] > feat_bound) feat_bound = float(B3[co]);
+    }
+  }
+  out->feat_bound = feat_bound;
+
+  static const char* hname[3] = {"64", "32", "16"};
+  const int n1[3] = {64, 128, 256}, n2[3] = {48, 96, 192}, n3[3] = {1, 4, 16};
+  const int col_off[3] = {0, 64, 192};
+  out->w1.assign(size_t(kFeat) * kFc1, 0.f);
+  out->b1.assign(kFc1, 0.f);
+  float wmax = 0.f;
+  for (int h = 0; h < 3; ++h) {
+    const std::string hs = hname[h];
+    const BundleTensor* w1 = find(t, "h_fc1__" + hs + "__w", {kFeat, n1[h]}, err);
+    const BundleTensor* b1 = find(t, "h_fc1__" + hs + "__b", {n1[h]}, err);
+    const BundleTensor* w2 = find(t, "h_fc2__" + hs + "__w", {n1[h] + 1, n2[h]}, err);
+    const BundleTensor* b2 = find(t, "h_fc2__" + hs + "__b", {n2[h]}, err);
+    const BundleTensor* w3 = find(t, "y_conv_flat__" + hs + "__w", {n2[h] + 1, n3[h]}, err);
+    const BundleTensor* b3 = find(t, "y_conv_flat__" + hs + "__b", {n3[h]}, err);
+    if (!w1 || !b1 || !w2 || !b2 || !w3 || !b3) return false;
+    for (int k = 0; k < kFeat; ++k)
+      for (int j = 0; j < n1[h]; ++j) {
+        const float w = w1->data[size_t(k) * n1[h] + j];
+        out->w1[size_t(k) * kFc1 + col_off[h] + j] = w;
+        if (std::fabs(w) > wmax) wmax = std::fabs(w);
+      }
+    memcpy(out->b1.data() + col_off[h], b1->data.data(), n1[h] * 4);
+    // the qp input is the LAST row of the FC2 / FC3 matrices (tf.concat([h, qp], axis=1), net_CNN.py:158,161)
+    out->w2[h].assign(w2->data.begin(), w2->data.begin() + size_t(n1[h]) * n2[h]);
+    out->w2q[h].assign(w2->data.begin() + size_t(n1[h]) * n2[h], w2->data.end());
+    out->b2[h] = b2->data;
+    out->w3[h].assign(w3->data.begin(), w3->data.begin() + size_t(n2[h]) * n3[h]);
+    out->w3q[h].assign(w3->data.begin() + size_t(n2[h]) * n3[h], w3->data.end());
+    out->b3[h] = b3->data;
+  }
+  for (float v : out->w1)
+    if (!std::isfinite(v)) {
+      *err = "non-finite FC1 weight";
+      return false;
+    }
+  if (!std::isfinite(feat_bound) || feat_bound <= 0.f) {
+    *err = "non-finite conv weights";
+    return false;
+  }
+
+  // power-of-two scales so that fp16 hi parts stay below 2^15 and lo parts stay normal for all but tiny values
+  auto pick_exp = [](float bound) {
+    int e = int(std::floor(std::log2(32768.0 / double(bound))));
+    if (e > 14) e = 14;
+    if (e < -14) e = -14;
+    return e;
+  };
+  out->feat_exp = pick_exp(feat_bound);
+  out->w_exp = pick_exp(wmax > 0.f ? wmax : 1.f);
+  const float ws = std::ldexp(1.0f, out->w_exp);
+  out->w1_hi.resize(size_t(kFc1) * kFeat);
+  out->w1_lo.resize(size_t(kFc1) * kFeat);
+  for (int k = 0; k < kFeat; ++k)
+    for (int j = 0; j < kFc1; ++j) {
+      const float s = out->w1[size_t(k) * kFc1 + j] * ws;
+      const uint16_t hi = f32_to_f16_bits(s);
+      const float lo = s - f16_bits_to_f32(hi);
+      out->w1_hi[size_t(j) * kFeat + k] = hi;
+      out->w1_lo[size_t(j) * kFeat + k] = f32_to_f16_bits(lo);
+    }
+  return true;
+}
+
+}  // namespace ethcnn

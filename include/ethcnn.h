@@ -1,0 +1,157 @@
+/*
+ * ethcnn.h -- C ABI of libethcnn_b200.so, the B200-native ETH-CNN CU-partition predictor.
+ *
+ * The reference (tianyili2017/HEVC-Complexity-Reduction) has no C API for this path: the patched HM
+ * encoder shells out to a Python script and reads a file back.  The entry points below are what a
+ * binding for that path would call; each cites the reference interface it replaces (paths relative
+ * to the reference root).  All functions are blocking unless stated, return 0 on success and a
+ * negative ETHCNN_E_* code on failure; ethcnn_last_error() returns the message of the last failure
+ * on the calling thread.  No CPU fallback exists: without a CUDA device every compute entry point
+ * fails with ETHCNN_E_CUDA.
+ */
+#ifndef ETHCNN_H_
+#define ETHCNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ETHCNN_ABI_VERSION 1
+
+/* Which network/deployment is evaluated. */
+#define ETHCNN_MODE_AI  0 /* HM-16.5_Test_AI/bin/net_CNN.py:103-195 (x/255, qp/51, batch-level gates)      */
+#define ETHCNN_MODE_LDP 1 /* ETH-CNN_Training_LDP/net_CTU64.py:100-179 ((x-128)/255*10, qp/51*0.18, no gates) */
+
+#define ETHCNN_OK            0
+#define ETHCNN_E_ARG        -1 /* bad argument (python: AssertionError at video_to_cu_depth.py:120,137) */
+#define ETHCNN_E_IO         -2 /* file missing / unreadable / short write                              */
+#define ETHCNN_E_FORMAT     -3 /* checkpoint or Thr_info.txt malformed (python: saver.restore raises)   */
+#define ETHCNN_E_CUDA       -4 /* CUDA runtime/driver failure or no device                             */
+#define ETHCNN_E_NOMEM      -5
+
+#define ETHCNN_PROBS_PER_CTU 21  /* video_to_cu_depth.py:63: y64(1) | y32(4) | y16(16) */
+#define ETHCNN_FC1_WIDTH     448 /* HM-16.5_Test_LDP/bin/net_CNN_LSTM_one_step.py:187-199 */
+
+typedef struct ethcnn_handle ethcnn_handle;
+
+/*
+ * Replaces the module-level set-up of video_to_cu_depth.py:14-29 and net_CNN.py:38-47: opens the
+ * device(s), reads Thr_info.txt (tokens [1] and [3], split on single spaces) and remembers where the
+ * TF-Saver-V2 checkpoints live.  Checkpoints are parsed, packed and uploaded on first use of their
+ * QP range (video_to_cu_depth.py:126-133) and stay resident.
+ *   model_dir  directory holding model_2000000_qp{20~25,25~30,30~35,35~40}.dat.{index,data-00000-of-00001}
+ *              (AI) or model_LDP_2000000_qp22~37.dat.* (LDP); the reference uses the cwd, i.e. ".".
+ *   thr_path   path of Thr_info.txt; NULL = <model_dir>/Thr_info.txt.  Ignored for ETHCNN_MODE_LDP.
+ *   n_gpus     >= 1: use CUDA devices 0..n_gpus-1, frames are sharded across them in contiguous
+ *              ranges and gathered into the caller's buffer (single process, HM forks one child).
+ */
+int ethcnn_create(const char* model_dir, const char* thr_path, int mode, int n_gpus, ethcnn_handle** out);
+
+/* As ethcnn_create with n_gpus = 1 but on an explicit CUDA device: the one-process-per-GPU form used
+ * under torchrun / torch.distributed (rank r opens device LOCAL_RANK). */
+int ethcnn_create_on_device(const char* model_dir, const char* thr_path, int mode, int device, ethcnn_handle** out);
+
+void ethcnn_destroy(ethcnn_handle* h);
+
+/*
+ * Replaces the whole script run `python video_to_cu_depth.py <yuv> <W> <H> <QP>`
+ * (HM-16.5_Test_AI/source/App/TAppEncoder/TAppEncCfg.cpp:2317-2321; video_to_cu_depth.py:120-145):
+ * reads every frame of the 8-bit 4:2:0 planar file (luma only), and writes out_path ("cu_depth.dat"
+ * in the reference) as n_frames * ceil(W/64) * ceil(H/64) * 21 little-endian float32, frame-major, CTU
+ * raster order, no header (consumer: TLibEncoder/TEncCu.cpp:257-258,434-447).  Fails with ETHCNN_E_ARG
+ * when file_bytes % (W*H*3/2) != 0 (video_to_cu_depth.py:137).  The output is written to a temporary
+ * file and renamed, so a failure never leaves a truncated cu_depth.dat.
+ */
+int ethcnn_predict_yuv_file(ethcnn_handle* h, const char* yuv_path, int width, int height, int qp,
+                            const char* out_path);
+
+/*
+ * Replaces get_prob() (video_to_cu_depth.py:75-118) for luma already in HOST memory.
+ *   y            first luma sample of frame 0; rows are `width` bytes, contiguous
+ *   frame_stride bytes between the first luma samples of consecutive frames (W*H*3/2 for a YUV 4:2:0
+ *                buffer, W*H for luma-only)
+ *   out          n_frames * nCTU * 21 floats (host)
+ * Pinned (page-locked) buffers are copied directly; pageable ones are staged through the library's
+ * own pinned ring.  Host<->device copies are pipelined against the kernels.
+ */
+int ethcnn_predict_luma(ethcnn_handle* h, const uint8_t* y, int width, int height, size_t frame_stride,
+                        int n_frames, int qp, float* out);
+
+/*
+ * Same computation with DEVICE pointers on the handle's (first) device, enqueued on `stream`
+ * (a cudaStream_t passed as void*; NULL = the legacy default stream) and NOT synchronised: the
+ * kernel-only path used for roofline measurement and by callers that keep frames resident.
+ *   pitch        bytes between rows (>= width).  pitch % 16 == 0, frame_stride % 16 == 0 and a 16-byte
+ *                aligned d_y select the TMA tile loader; anything else falls back to a plain-load
+ *                variant of the same kernel (still on the GPU).
+ *   d_out        n_frames * nCTU * 21 floats (device)
+ */
+int ethcnn_predict_luma_device(ethcnn_handle* h, const uint8_t* d_y, int width, int height, size_t pitch,
+                               size_t frame_stride, int n_frames, int qp, float* d_out, void* stream);
+
+/*
+ * LDP deployment tap: the 448-vector [fc1_64 | fc1_32 | fc1_16] that resi_cnn() hands to the LSTM
+ * (HM-16.5_Test_LDP/bin/net_CNN_LSTM_one_step.py:151-199).  Host pointers; out has
+ * n_frames * nCTU * 448 floats.  Requires ETHCNN_MODE_LDP.
+ */
+int ethcnn_export_fc1(ethcnn_handle* h, const uint8_t* y, int width, int height, size_t frame_stride,
+                      int n_frames, float* out);
+
+/* HM's use of a probability (TLibEncoder/TEncCu.cpp:448-462): 2 = split only (p > up), 0 = no split
+ * (p <= down), 1 = check both.  thr6 = the six numbers of Thr_info.txt (up,down per depth,
+ * TEncCu.cpp:250).  Runs on the device; prob/decision are HOST arrays of n_ctus*21 entries. */
+int ethcnn_decisions(ethcnn_handle* h, const float* prob, size_t n_ctus, const float thr6[6], uint8_t* decision);
+
+/* Introspection (for bench.py and tests). */
+#define ETHCNN_Q_KERNEL_LAUNCHES   1 /* kernels launched by this handle since creation            */
+#define ETHCNN_Q_N_DEVICES         2
+#define ETHCNN_Q_FC1_PATH          3 /* 1 = tcgen05 tensor-core FC1, 0 = SIMT fp32 FC1            */
+#define ETHCNN_Q_TMA_LOADER_USED   4 /* 1 if the last device call used the TMA tile loader         */
+#define ETHCNN_Q_SM_COUNT          5
+int ethcnn_query(ethcnn_handle* h, int what, int64_t* value);
+
+/* Per-kernel device timing: when enabled, every launch is bracketed by CUDA events on the launching
+ * stream; ethcnn_profile_read() synchronises and returns, for stage s (ETHCNN_STAGE_*), the summed
+ * milliseconds and launch count since the last reset. */
+#define ETHCNN_STAGE_CONV   0 /* luma tiles -> 2688 features (conv stack)   */
+#define ETHCNN_STAGE_FC1    1 /* 2688 -> 448 dense contraction              */
+#define ETHCNN_STAGE_HEADS  2 /* FC2 + FC3 + sigmoid                        */
+#define ETHCNN_STAGE_GATE   3 /* per-sub-batch gates                        */
+#define ETHCNN_N_STAGES     4
+int ethcnn_profile_enable(ethcnn_handle* h, int on);
+int ethcnn_profile_read(ethcnn_handle* h, int stage, double* ms_total, int64_t* launches, int reset);
+
+/* Tuning knobs (before the first predict call): see ETHCNN_OPT_*. */
+#define ETHCNN_OPT_FC1_PATH    1 /* 0 = SIMT fp32, 1 = tcgen05 (default)            */
+#define ETHCNN_OPT_CHUNK_CTUS  2 /* CTUs per feature-buffer chunk                    */
+int ethcnn_set_option(ethcnn_handle* h, int option, int64_t value);
+
+/* Pinned host memory helpers (so foreign-language callers can hand over page-locked buffers). */
+void* ethcnn_alloc_pinned(size_t bytes);
+void ethcnn_free_pinned(void* p);
+
+/* Host-side testing hooks (no GPU needed): the checkpoint reader + weight packer and the Thr_info.txt
+ * parser, exposed so the CPU test-suite can check them against the oracle.
+ *   conv     3 * 4952 floats  (branch S, M, L blocks in the shared-memory layout of csrc/kernels.h)
+ *   w1       2688 * 448 floats (heads 64 | 32 | 16 side by side), b1 448 floats
+ *   w1_hi/lo 448 * 2688 fp16 bit patterns of w1 * 2^exps[1] (K-major), exps = {feat_exp, w_exp}
+ * Any output pointer may be NULL. */
+int ethcnn_debug_pack_model(const char* ckpt_prefix, float input_bound, float* conv, float* w1, float* b1,
+                            uint16_t* w1_hi, uint16_t* w1_lo, int exps[2], float* feat_bound);
+int ethcnn_debug_read_thresholds(const char* thr_path, float thr[2]);
+uint16_t ethcnn_debug_f32_to_f16(float v);
+/* Device-side testing hook: copy back intermediates of the LAST chunk processed on device 0.
+ * what = 0: the 2688 conv features per CTU (hi + lo halves recombined and unscaled), out[n_ctus*2688];
+ * what = 1: the FC1 activations, out[n_ctus*448].  n_ctus must not exceed the chunk size. */
+int ethcnn_debug_read_scratch(ethcnn_handle* h, int what, size_t n_ctus, float* out);
+
+const char* ethcnn_last_error(void);
+int ethcnn_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ETHCNN_H_ */

@@ -221,6 +221,12 @@ def main():
         yuv = yuv_from_luma(list(ctus))  # 64x64 frames
         out["prob_qp%d" % q] = run_reference_script(yuv, 64, 64, q, "0.5 -1 0.5 -1 0.5 -1")  # gates always open
     np.savez_compressed(os.path.join(OUT, "ai_ctus_ungated.npz"), ctus=ctus, qps=np.array(QPS), **out)
+    # G. the two checkpoints the GPU box needs for real-weight parity, as {tensor name: float32 array}
+    # (re-serialised into TF bundles at test time by oracle/assets.materialize)
+    from oracle import assets, tf_bundle
+    for name, npz in assets.NPZ.items():
+        src = os.path.join(LDP_BIN if name == assets.LDP_MODEL else AI_BIN, name)
+        np.savez_compressed(os.path.join(OUT, npz), **tf_bundle.read_bundle(src, verify_crc=True))
     print("golden fixtures written to", OUT)
     for fn in sorted(os.listdir(OUT)):
         print("  %-32s %8d B" % (fn, os.path.getsize(os.path.join(OUT, fn))))

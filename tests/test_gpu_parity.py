@@ -1,0 +1,261 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the committed reference vectors.
+Bar: |dp| <= 1e-4 (BASELINE.json north_star) -- in practice a few 1e-6, asserted at 2e-5 -- and
+identical HM decisions after threshold quantisation; every flip would be listed with |p - thr|."""
+import glob
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import assets, tf_bundle
+from oracle import ethcnn_oracle as eo
+from test_oracle_golden import golden_input
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL = 1e-4          # the contract
+TIGHT = 2e-5        # what two fp32 evaluation orders are expected to reach
+
+
+def check(got, want, thr6=(0.5,) * 6, tol=TIGHT, what=""):
+    assert got.shape == want.shape, what
+    err = np.abs(got.astype(np.float64) - want.astype(np.float64))
+    assert err.max() <= TOL, "%s: max|dp| = %g exceeds the 1e-4 contract" % (what, err.max())
+    assert err.max() <= tol, "%s: max|dp| = %g" % (what, err.max())
+    dg, dw = eo.decisions(got, thr6), eo.decisions(want, thr6)
+    flips = np.argwhere(dg != dw)
+    msg = "; ".join("ctu %d slot %d p_cuda=%.7f p_oracle=%.7f" % (i, j, got[i, j], want[i, j]) for i, j in flips[:10])
+    assert len(flips) == 0, "%s: %d decision flips: %s" % (what, len(flips), msg)
+    assert np.array_equal(got == 0, want == 0), "%s: gated zeros differ" % what
+    return float(err.max())
+
+
+@pytest.fixture(scope="module")
+def net(eb, ai_model_dir):
+    d, present = ai_model_dir
+    n = eb.EthCnn(d, None, eb.MODE_AI, device=0)
+    yield n
+    n.close()
+
+
+def test_reference_vectors_ai(net, golden_dir, ai_model_dir, eb):
+    d, present = ai_model_dir
+    seen = 0
+    for fn in sorted(glob.glob(os.path.join(golden_dir, "ai_*.npz"))):
+        g = np.load(fn)
+        for qp in g["qps"]:
+            qp = int(qp)
+            if assets.AI_MODELS[qp] not in present:
+                continue
+            yuv, W, H, thr = golden_input(g)
+            if thr != (0.5, 0.5):   # non-default Thr_info.txt -> its own handle
+                td = d + "_thr_%s" % os.path.basename(fn)
+                assets.materialize(td, "AI", thr_line=str(g["thr_line"]) if "thr_line" in g.files else "0.5 -1 0.5 -1 0.5 -1")
+                with eb.EthCnn(td, None, eb.MODE_AI, device=0) as n2:
+                    got = n2.predict_yuv_buffer(np.frombuffer(yuv, np.uint8), W, H, qp)
+            else:
+                got = net.predict_yuv_buffer(np.frombuffer(yuv, np.uint8), W, H, qp)
+            check(got, g["prob_qp%d" % qp], what="%s qp%d" % (os.path.basename(fn), qp))
+            seen += 1
+    assert seen >= 6
+
+
+def test_reference_vectors_ldp(eb, ldp_model_dir, golden_dir):
+    d, present = ldp_model_dir
+    assert assets.LDP_MODEL in present
+    g = np.load(os.path.join(golden_dir, "ldp_ctus.npz"))
+    with eb.EthCnn(d, None, eb.MODE_LDP, device=0) as net:
+        for qp in g["qps"]:
+            got = net.predict_ctus(g["ctus"], int(qp))
+            check(got, g["prob_qp%d" % qp], what="ldp qp%d" % qp)
+        fc1 = net.export_fc1(g["ctus"].reshape(-1, 4096), 64, 64, g["ctus"].shape[0])
+        ref = g["fc1_vector"]
+        assert np.abs(fc1 - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("fc1_path", [1, 0])
+@pytest.mark.parametrize("seed", [1, 2])
+def test_synthetic_weights_vs_oracle(eb, tmp_path, fc1_path, seed):
+    """Random checkpoints in the reference's 36-tensor layout: a layout/ordering mistake cannot hide behind
+    trained-weight structure.  Both FC1 implementations (tcgen05 and SIMT) are held to the same bar."""
+    w = eo.random_weights(seed)
+    d = str(tmp_path)
+    for name in assets.AI_MODELS.values():
+        tf_bundle.write_bundle(os.path.join(d, name), w)
+    open(os.path.join(d, "Thr_info.txt"), "w").write("0.5 0.5 0.5 0.5 0.5 0.5")
+    W, H, nf = 456, 264, 3
+    yuv = eo.synth_yuv(W, H, nf, seed0=10 * seed)
+    with eb.EthCnn(d, None, eb.MODE_AI, device=0) as net:
+        net.set_option(1, fc1_path)
+        for qp in (22, 37):
+            got = net.predict_yuv_buffer(np.frombuffer(yuv, np.uint8), W, H, qp)
+            want = eo.get_prob(yuv, W, H, qp, w, eo.MODE_AI, (0.5, 0.5))
+            check(got, want, what="synthetic seed %d qp %d fc1 %d" % (seed, qp, fc1_path))
+        assert net.query(3) == fc1_path
+
+
+def test_fp64_oracle_agreement(net, ai_model_dir):
+    """Against the fp64 oracle the CUDA path must be as good as the fp32 oracle is (noise floor ~5e-6)."""
+    d, present = ai_model_dir
+    w = assets.load_weights(assets.AI_MODELS[32])
+    W, H = 1920, 1080
+    yuv = eo.synth_yuv(W, H, 1, seed0=77)
+    got = net.predict_yuv_buffer(np.frombuffer(yuv, np.uint8), W, H, 32)
+    p64 = eo.get_prob(yuv, W, H, 32, w, eo.MODE_AI, (0.5, 0.5), dtype=np.float64)
+    p32 = eo.get_prob(yuv, W, H, 32, w, eo.MODE_AI, (0.5, 0.5), dtype=np.float32)
+    e_cuda = np.abs(got - p64).max()
+    e_f32 = np.abs(p32.astype(np.float64) - p64).max()
+    assert e_cuda <= max(1e-5, 4 * e_f32), (e_cuda, e_f32)
+
+
+def test_chunking_and_loader_variants_are_bit_identical(eb, ai_model_dir):
+    import torch
+
+    d, _ = ai_model_dir
+    W, H, nf, qp = 712, 328, 5, 32           # 12 x 6 = 72 CTUs per frame, padded both ways; 712 % 16 == 8
+    yuv = np.frombuffer(eo.synth_yuv(W, H, nf, seed0=5), np.uint8)
+    with eb.EthCnn(d, None, eb.MODE_AI, device=0) as net:
+        base = net.predict_yuv_buffer(yuv, W, H, qp)
+        net.set_option(2, 100)                # chunk boundary inside frames and inside tile groups
+        assert np.array_equal(net.predict_yuv_buffer(yuv, W, H, qp), base)
+        net.set_option(2, 148 * 128)
+        # device entry point: TMA loader (aligned pitch) vs plain-load loader (pitch = W, not 16-aligned)
+        luma = np.stack([yuv.reshape(nf, -1)[k, :W * H].reshape(H, W) for k in range(nf)])
+        out = torch.empty((nf * 72, 21), dtype=torch.float32, device="cuda")
+        for pitch, expect_tma in ((720, 1), (W, 0)):
+            buf = torch.zeros((nf, H, pitch), dtype=torch.uint8, device="cuda")
+            buf[:, :, :W] = torch.from_numpy(luma).cuda()
+            out.zero_()
+            s = torch.cuda.current_stream().cuda_stream
+            net.predict_luma_device(buf.data_ptr(), W, H, pitch, H * pitch, nf, qp, out.data_ptr(), s)
+            torch.cuda.synchronize()
+            assert net.query(4) == expect_tma
+            assert np.array_equal(out.cpu().numpy(), base), "pitch %d" % pitch
+
+
+def test_repeatability_and_frame_independence(net):
+    W, H, nf, qp = 1920, 1080, 4, 32
+    yuv = np.frombuffer(eo.synth_yuv(W, H, nf, seed0=40), np.uint8)
+    a = net.predict_yuv_buffer(yuv, W, H, qp)
+    b = net.predict_yuv_buffer(yuv, W, H, qp)
+    assert np.array_equal(a, b)
+    # frames are independent units: predicting frames in reverse order permutes the rows
+    fb = W * H * 3 // 2
+    rev = np.concatenate([yuv[k * fb:(k + 1) * fb] for k in reversed(range(nf))])
+    c = net.predict_yuv_buffer(rev, W, H, qp).reshape(nf, -1, 21)[::-1].reshape(-1, 21)
+    assert np.array_equal(a, c)
+    assert a.shape == (nf * 510, 21) and np.isfinite(a).all() and a.min() >= 0 and a.max() <= 1
+
+
+def test_full_size_config2_and_config3_frames_vs_oracle(net):
+    """BASELINE config 2 (1920x1080) and config 3 (4928x3264: sub-batches 1024/1024/1024/855) frames."""
+    w = assets.load_weights(assets.AI_MODELS[32])
+    for (W, H) in ((1920, 1080), (4928, 3264)):
+        yuv = eo.synth_yuv(W, H, 1, seed0=3)
+        got = net.predict_yuv_buffer(np.frombuffer(yuv, np.uint8), W, H, 32)
+        want = eo.get_prob(yuv, W, H, 32, w, eo.MODE_AI, (0.5, 0.5))
+        check(got, want, what="%dx%d" % (W, H))
+
+
+def test_flat_and_noise_frames(net):
+    """Degenerate content: a flat frame closes both gates, uniform noise saturates."""
+    w = assets.load_weights(assets.AI_MODELS[32])
+    W, H = 256, 192
+    flat = np.full((H, W), 128, np.uint8)
+    rng = np.random.default_rng(0)
+    noise = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    checker = ((np.indices((H, W)).sum(0) // 8) % 2 * 255).astype(np.uint8)
+    yuv = b"".join(f.tobytes() + bytes([128]) * (W * H // 2) for f in (flat, noise, checker))
+    got = net.predict_yuv_buffer(np.frombuffer(yuv, np.uint8), W, H, 32)
+    want = eo.get_prob(yuv, W, H, 32, w, eo.MODE_AI, (0.5, 0.5))
+    check(got, want, what="degenerate frames")
+    assert (got[:12, 1:] == 0).all()
+
+
+def test_yuv_file_entry_point_and_cli(eb, ai_model_dir, tmp_path):
+    d, _ = ai_model_dir
+    W, H, nf, qp = 200, 136, 2, 32
+    yuv = eo.synth_yuv(W, H, nf, seed0=100)
+    src = tmp_path / "clip.yuv"
+    src.write_bytes(yuv)
+    w = assets.load_weights(assets.AI_MODELS[32])
+    want = eo.get_prob(yuv, W, H, qp, w, eo.MODE_AI, (0.5, 0.5))
+    with eb.EthCnn(d, None, eb.MODE_AI, device=0) as net:
+        out = tmp_path / "cu_depth.dat"
+        net.predict_yuv_file(str(src), W, H, qp, str(out))
+        got = np.fromfile(out, dtype="<f4").reshape(-1, 21)
+        check(got, want, what="yuv file")
+        assert out.stat().st_size == nf * 12 * 21 * 4
+        # size not a whole number of frames -> error, and the previous cu_depth.dat is left untouched
+        (tmp_path / "bad.yuv").write_bytes(yuv[:-7])
+        before = out.read_bytes()
+        with pytest.raises(eb.EthCnnError) as e:
+            net.predict_yuv_file(str(tmp_path / "bad.yuv"), W, H, qp, str(out))
+        assert e.value.code == -1 and out.read_bytes() == before
+        with pytest.raises(eb.EthCnnError) as e:
+            net.predict_yuv_file(str(tmp_path / "absent.yuv"), W, H, qp, str(out))
+        assert e.value.code == -2
+    # the CLI with the reference's argv, run from a cwd laid out like the encoder's
+    cli = os.path.join(ROOT, "hevc-complexity-reduction_b200", "bin", "video_to_cu_depth")
+    r = subprocess.run([cli, str(src), str(W), str(H), str(qp)], cwd=d, capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    assert b"Predicting Time" in r.stdout
+    cli_out = np.fromfile(os.path.join(d, "cu_depth.dat"), dtype="<f4").reshape(-1, 21)
+    assert np.array_equal(cli_out, got)
+    os.remove(os.path.join(d, "cu_depth.dat"))
+    # the python drop-in script (what the unmodified HM binary launches)
+    script = os.path.join(ROOT, "hevc-complexity-reduction_b200", "video_to_cu_depth.py")
+    r = subprocess.run(["python", script, str(src), str(W), str(H), str(qp)], cwd=d, capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    assert np.array_equal(np.fromfile(os.path.join(d, "cu_depth.dat"), dtype="<f4").reshape(-1, 21), got)
+    os.remove(os.path.join(d, "cu_depth.dat"))
+    r = subprocess.run(["python", script, str(tmp_path / "bad.yuv"), str(W), str(H), str(qp)], cwd=d, capture_output=True)
+    assert r.returncode != 0 and not os.path.exists(os.path.join(d, "cu_depth.dat"))
+
+
+def test_missing_checkpoint_is_an_io_error(eb, tmp_path):
+    open(tmp_path / "Thr_info.txt", "w").write("0.5 0.5 0.5 0.5 0.5 0.5")
+    with eb.EthCnn(str(tmp_path), None, eb.MODE_AI, device=0) as net:
+        with pytest.raises(eb.EthCnnError) as e:
+            net.predict_ctus(np.zeros((1, 64, 64), np.uint8), 32)
+        assert e.value.code == -2
+
+
+def test_empty_input(net):
+    out = net.predict_luma(np.zeros(0, np.uint8), 64, 64, 0, 32)
+    assert out.shape == (0, 21)
+
+
+def test_decision_kernel_matches_consumer_rule(net):
+    rng = np.random.default_rng(1)
+    p = rng.random((1000, 21), dtype=np.float32)
+    p[0, :3] = [0.5, np.nextafter(np.float32(0.5), np.float32(1)), np.nextafter(np.float32(0.5), np.float32(0))]
+    for thr6 in ((0.5,) * 6, (0.9, 0.1, 0.8, 0.2, 0.7, 0.3)):
+        assert np.array_equal(net.decisions(p, thr6), eo.decisions(p, thr6))
+
+
+def test_pinned_and_pageable_hosts_agree(eb, ai_model_dir):
+    import torch
+
+    d, _ = ai_model_dir
+    W, H, nf, qp = 1920, 1080, 6, 32
+    yuv = np.frombuffer(eo.synth_yuv(W, H, nf, seed0=9), np.uint8)
+    with eb.EthCnn(d, None, eb.MODE_AI, device=0) as net:
+        a = net.predict_yuv_buffer(yuv, W, H, qp)
+        pin = torch.from_numpy(yuv.copy()).pin_memory()
+        out = torch.empty((nf * 510, 21), dtype=torch.float32).pin_memory()
+        net.predict_luma_ptr(pin.data_ptr(), W, H, W * H * 3 // 2, nf, qp, out.data_ptr())
+        assert np.array_equal(out.numpy(), a)
+
+
+def test_in_library_multi_gpu_matches_single(eb, ai_model_dir):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    d, _ = ai_model_dir
+    W, H, nf, qp = 1920, 1080, 7, 32
+    yuv = np.frombuffer(eo.synth_yuv(W, H, nf, seed0=2), np.uint8)
+    with eb.EthCnn(d, None, eb.MODE_AI, n_gpus=1) as n1, eb.EthCnn(d, None, eb.MODE_AI, n_gpus=2) as n2:
+        assert np.array_equal(n1.predict_yuv_buffer(yuv, W, H, qp), n2.predict_yuv_buffer(yuv, W, H, qp))

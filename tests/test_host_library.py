@@ -1,0 +1,179 @@
+"""CPU-side checks of the product's host code through the C ABI: the library loads and exports every
+symbol include/ethcnn.h declares, the C++ TF-bundle reader + weight packer agree with the oracle's
+independent reader, Thr_info.txt parsing follows net_CNN.py:38-45, and error behaviour (no compute
+without a GPU; non-zero exit codes)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import assets, tf_bundle
+from oracle import ethcnn_oracle as eo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol(eb):
+    lib = eb.load_library()
+    hdr = open(os.path.join(ROOT, "include", "ethcnn.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(ethcnn_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 19
+    for n in names:
+        assert hasattr(lib, n), "library lacks %s declared in include/ethcnn.h" % n
+    assert lib.ethcnn_abi_version() == 1
+
+
+def test_missing_library_fails_loudly(eb, monkeypatch, tmp_path):
+    from hevc_complexity_reduction_b200 import binding
+    monkeypatch.setattr(binding, "_LIB", None)
+    monkeypatch.setenv("ETHCNN_LIB", str(tmp_path / "nope.so"))
+    with pytest.raises(eb.EthCnnError):
+        binding.load_library()
+
+
+def _pack(eb, prefix, input_bound=1.0):
+    lib = eb.load_library()
+    conv = np.zeros(3 * 4952, np.float32)
+    w1 = np.zeros((2688, 448), np.float32)
+    b1 = np.zeros(448, np.float32)
+    hi = np.zeros((448, 2688), np.uint16)
+    lo = np.zeros((448, 2688), np.uint16)
+    exps = np.zeros(2, np.int32)
+    fb = np.zeros(1, np.float32)
+    rc = lib.ethcnn_debug_pack_model(prefix.encode(), C.c_float(input_bound), *[C.c_void_p(a.ctypes.data) for a in
+                                                                                   (conv, w1, b1, hi, lo, exps, fb)])
+    return rc, conv.reshape(3, 4952), w1, b1, hi, lo, exps, float(fb[0])
+
+
+@pytest.mark.parametrize("which", ["real", "synthetic"])
+def test_cpp_reader_and_packer_match_oracle(eb, tmp_path, which):
+    if which == "real":
+        d = str(tmp_path)
+        assets.materialize(d, "AI")
+        prefix = os.path.join(d, assets.AI_MODELS[32])
+        w = assets.load_weights(assets.AI_MODELS[32])
+    else:
+        w = eo.random_weights(11)
+        prefix = str(tmp_path / "m.dat")
+        tf_bundle.write_bundle(prefix, w)
+    rc, conv, w1, b1, hi, lo, exps, fbound = _pack(eb, prefix)
+    assert rc == 0, eb.load_library().ethcnn_last_error()
+    # conv blocks: branch order S, M, L <- Variable_12.., Variable_6.., Variable..
+    for br, base in enumerate((12, 6, 0)):
+        v = lambda i: w["Variable" if base + i == 0 else "Variable_%d" % (base + i)]
+        blk = conv[br]
+        assert np.array_equal(blk[0:256], v(0).reshape(-1))
+        assert np.array_equal(blk[256:272], v(1))
+        assert np.array_equal(blk[272:1808], v(2).reshape(-1))
+        assert np.array_equal(blk[1808:1832], v(3))
+        w3 = v(4).reshape(4, 768)
+        for d in range(4):
+            assert np.array_equal(blk[1832 + d * 772: 1832 + d * 772 + 768], w3[d])
+        assert np.array_equal(blk[4920:4952], v(5))
+    ref_w1 = np.concatenate([w["h_fc1__%s__w" % h] for h in ("64", "32", "16")], axis=1)
+    assert np.array_equal(w1, ref_w1)
+    assert np.array_equal(b1, np.concatenate([w["h_fc1__%s__b" % h] for h in ("64", "32", "16")]))
+    # hi/lo split reproduces the scaled weights to ~2^-22 relative
+    ws = np.float32(2.0 ** exps[1])
+    rec = (hi.view(np.float16).astype(np.float64) + lo.view(np.float16).astype(np.float64)).T / ws
+    assert np.abs(rec - ref_w1).max() <= np.abs(ref_w1).max() * 2.0 ** -21
+    assert np.abs(ref_w1).max() * ws < 65504 / 1.9
+    # feature bound is a true bound: oracle features on extreme content stay below it
+    ctus = np.concatenate([eo.known_answer_ctus(), (np.indices((64, 64)).sum(0) % 2 * 255).astype(np.uint8)[None]])
+    x, _ = eo.input_scaling(ctus, 32, eo.MODE_AI, np.float32)
+    f = eo.conv_features(x, w)
+    assert np.abs(f).max() <= fbound
+    assert fbound * 2.0 ** exps[0] <= 32768.0
+
+
+def test_cpp_reader_rejects_corruption(eb, tmp_path):
+    w = eo.random_weights(5)
+    prefix = str(tmp_path / "m.dat")
+    tf_bundle.write_bundle(prefix, w)
+    lib = eb.load_library()
+    assert _pack(eb, prefix)[0] == 0
+    data = bytearray(open(prefix + ".data-00000-of-00001", "rb").read())
+    data[1000] ^= 0x40
+    open(prefix + ".data-00000-of-00001", "wb").write(bytes(data))
+    assert _pack(eb, prefix)[0] == -3 and b"crc" in lib.ethcnn_last_error()
+    assert _pack(eb, str(tmp_path / "absent.dat"))[0] == -2
+    idx = bytearray(open(prefix + ".index", "rb").read())
+    idx[-1] ^= 0xFF
+    open(prefix + ".index", "wb").write(bytes(idx))
+    assert _pack(eb, prefix)[0] == -3 and b"magic" in lib.ethcnn_last_error()
+    # a checkpoint lacking a tensor
+    w2 = dict(w)
+    del w2["h_fc2__32__w"]
+    tf_bundle.write_bundle(prefix, w2)
+    assert _pack(eb, prefix)[0] == -3 and b"h_fc2__32__w" in lib.ethcnn_last_error()
+
+
+def test_f16_conversion_matches_numpy(eb):
+    lib = eb.load_library()
+    rng = np.random.default_rng(0)
+    vals = np.concatenate([
+        rng.standard_normal(2000).astype(np.float32) * np.float32(10.0) ** rng.integers(-9, 5, 2000).astype(np.float32),
+        np.array([0.0, -0.0, 65504.0, 65519.9, 65520.0, 1e6, -1e6, 6.1035156e-05, 6.0975552e-05, 5.9604645e-08,
+                  2.9802322e-08, 2.98023259e-08, 1.0, 1.00048828125, 1.0009765625, 0.33325195], dtype=np.float32)])
+    for v in vals:
+        want = np.float32(v).astype(np.float16).view(np.uint16)
+        got = lib.ethcnn_debug_f32_to_f16(C.c_float(float(v)))
+        assert int(got) == int(want), (float(v), hex(got), hex(int(want)))
+
+
+def test_threshold_parser_follows_python_split(eb, tmp_path):
+    p = tmp_path / "Thr_info.txt"
+    p.write_text("0.9 0.95 0.8 0.7 0.6 0.4")
+    assert eb.net_CNN.get_thresholds(str(p)) == pytest.approx((0.95, 0.7))
+    assert eo.get_thresholds(str(p)) == pytest.approx((0.95, 0.7))
+    p.write_text("0.5 0.25 0.5 0.125\n")                     # trailing newline on the 4th token is fine for float()
+    assert eb.net_CNN.get_thresholds(str(p)) == (0.25, 0.125)
+    p.write_text("0.5  0.25 0.5 0.125")                      # double space -> token[1] == '' -> float('') raises
+    with pytest.raises(eb.EthCnnError):
+        eb.net_CNN.get_thresholds(str(p))
+    with pytest.raises(ValueError):
+        eo.get_thresholds(str(p))
+    p.write_text("0.5 0.5")
+    with pytest.raises(eb.EthCnnError):
+        eb.net_CNN.get_thresholds(str(p))
+    with pytest.raises(eb.EthCnnError):
+        eb.net_CNN.get_thresholds(str(tmp_path / "missing.txt"))
+
+
+@pytest.mark.skipif(_has_gpu(), reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback(eb, ai_model_dir):
+    d, _ = ai_model_dir
+    with pytest.raises(eb.EthCnnError) as e:
+        eb.EthCnn(d)
+    assert e.value.code == -4 and "no CPU fallback" in str(e.value)
+
+
+def test_cli_usage_and_failure_exit_codes(tmp_path):
+    cli = os.path.join(ROOT, "hevc-complexity-reduction_b200", "bin", "video_to_cu_depth")
+    assert os.path.exists(cli), "CLI not built"
+    r = subprocess.run([cli, "a.yuv", "64"], capture_output=True, cwd=tmp_path)
+    assert r.returncode == 1 and b"usage" in r.stderr
+    r = subprocess.run([cli, "a.yuv", "sixty", "64", "32"], capture_output=True, cwd=tmp_path)
+    assert r.returncode == 1
+    # no Thr_info.txt in the cwd -> failure, and no cu_depth.dat left behind
+    r = subprocess.run([cli, "a.yuv", "64", "64", "32"], capture_output=True, cwd=tmp_path)
+    assert r.returncode == 1 and not os.path.exists(tmp_path / "cu_depth.dat")
+
+
+def test_python_drop_in_script_has_no_arithmetic():
+    src = open(os.path.join(ROOT, "hevc-complexity-reduction_b200", "video_to_cu_depth.py")).read()
+    assert "numpy" not in src and "oracle" not in src
+    for f in ("binding.py", "__init__.py", "net_CNN.py", "sharding.py"):
+        assert "oracle" not in open(os.path.join(ROOT, "hevc-complexity-reduction_b200", f)).read().replace("oracle/", "")
