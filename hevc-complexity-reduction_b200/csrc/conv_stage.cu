@@ -5,66 +5,93 @@
 //   per branch: conv 4x4/s4 1->16, conv 2x2/s2 16->24, conv 2x2/s2 24->32, leaky(0.2) after each
 //   features = [c3_S | c3_M | c3_L | c2_S | c2_M | c2_L], each NHWC-flattened.
 //
-// Work decomposition.  All three branches have the same shape once the input is pooled: a lane owns an
+// Work decomposition.  All three branches have the same shape once the input is pooled: a "region" is an
 // 8x8 block of (pooled) samples = 2x2 conv1 patches = one conv2 output position, and 2x2 neighbouring
-// lanes (a "quad") share one mean-removal window (16x16 pooled samples) and one conv3 output position.
-//   S: pool 1, lane region  8x8  px, 64 lanes per CTU -> a warp task covers half a CTU
-//   M: pool 2, lane region 16x16 px, 16 lanes per CTU -> a warp task covers 2 CTUs
-//   L: pool 4, lane region 32x32 px,  4 lanes per CTU -> a warp task covers 8 CTUs
-// so a group of 8 CTUs is exactly 16 + 4 + 1 = 21 warp tasks of identical cost.  Every lane of a warp
-// uses the same filter taps, so weights are broadcast 128-bit shared-memory loads and activations live
-// in registers; the quad exchanges data only through warp shuffles (window sums, conv3 reduce-scatter).
+// regions (a "quad", held by 4 adjacent lanes) share one mean-removal window (16x16 pooled samples) and
+// one conv3 output position.
+//   S: pool 1, region  8x8  px, 64 regions per CTU      M: pool 2, 16x16 px, 16 per CTU
+//   L: pool 4, region 32x32 px,  4 regions per CTU
+// Every lane owns TWO regions (A and B) that use the same filter taps, so each weight fetched from shared
+// memory feeds two packed FMAs (fma.rn.f32x2: two output channels at once) -- a broadcast 128-bit LDS
+// costs two shared-memory wavefronts, and at one region per lane the kernel was bound by that pipe and by
+// instruction fetch (round-1 ncu: 52 % LSU wavefronts, 46 % I-cache misses).  A warp task is therefore
+// one CTU (S), four CTUs (M) or sixteen CTUs (L); a group of 16 CTUs is exactly 16 + 4 + 1 = 21 warp
+// tasks of identical cost.  One code body serves the three branches (the pool factor only changes the
+// small integer-sum loaders), conv3 is rolled over its four 8-channel output groups, and the whole hot
+// loop stays inside the 32 KB instruction cache.
 //
 // Mean removal is exact: with s = pooled integer sum and W = integer sum of the whole window,
 //   pooled - mean = (256*s - W) / (256*pool^2), one rounding when multiplied by scale/(256*pool^2).
 //
 // A persistent CTA (one per SM) keeps the 58 KB of conv weights resident in shared memory and streams
-// 8-CTU tile groups through a 4-deep TMA ring (3-D tensor map over (x, y, frame), 64x64x1 box; the
-// zero fill of out-of-bounds rows/columns IS the reference's zero padding, video_to_cu_depth.py:54-57).
+// 16-CTU tile groups through a 2-deep TMA ring (3-D tensor map over (x, y, frame), 64x64x1 box; the zero
+// fill of out-of-bounds rows/columns IS the reference's zero padding, video_to_cu_depth.py:54-57).
 // One producer warp issues TMA, eleven compute warps take warp tasks round-robin.
+#include <cstring>
+
 #include "kernels.h"
 #include "ptx_sm100.cuh"
 
 namespace ethcnn {
 namespace {
 
-// 128-bit shared-memory load of four consecutive weights.  `asm volatile` on purpose: the conv1 filter is
-// invariant across the patch loop and the compiler would otherwise hoist all 64 loads (256 registers).
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
+// 128-bit shared-memory load of four consecutive weights as two channel pairs.  `asm volatile` on
+// purpose: the conv1 filter is invariant across the patch loop and the compiler would otherwise hoist
+// all 64 loads (256 registers).
+__device__ __forceinline__ void lds_pairs(uint32_t addr, float2& p0, float2& p1) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(p0.x), "=f"(p0.y), "=f"(p1.x), "=f"(p1.y) : "r"(addr));
 }
 
 __device__ __forceinline__ float leaky(float v) { return fmaxf(0.2f * v, v); }  // Maximum(alpha*x, x), alpha = 0.2
+__device__ __forceinline__ float2 leaky2(float2 v) { return make_float2(leaky(v.x), leaky(v.y)); }
+__device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// value * scale -> (hi, lo) fp16 pair with hi + lo == value*scale to ~22 bits
-__device__ __forceinline__ void split_hi_lo(float v, float scale, float& hi, float& lo) {
-  float s = v * scale;
-  hi = __half2float(__float2half_rn(s));
-  lo = s - hi;
+// (v.x, v.y) * scale -> packed fp16 hi pair and lo pair with hi + lo == v * scale to ~22 bits
+__device__ __forceinline__ void split_pair(float2 v, float scale, uint32_t& hi, uint32_t& lo) {
+  const float sx = v.x * scale, sy = v.y * scale;
+  const __half2 h = __floats2half2_rn(sx, sy);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = pack_half2(sx - __low2float(h), sy - __high2float(h));
 }
 
-// Integer sum of the lane's whole region ((8P) x (8P) pixels at reg0, row pitch 64).
-template <int P>
-__device__ __forceinline__ uint32_t region_sum(const uint8_t* __restrict__ reg0) {
+// Explicit shared-memory loads of pixels (32-bit shared addresses keep the compiler from emitting generic LD).
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint2 lds_u64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+// Integer sum of a whole region ((8*pool) x (8*pool) pixels at shared address reg0, row pitch 64).
+__device__ __forceinline__ uint32_t region_sum(int pool, uint32_t reg0) {
   uint32_t s = 0;
+  if (pool == 1) {
 #pragma unroll
-  for (int r = 0; r < 8 * P; ++r) {
-    const uint8_t* row = reg0 + r * kCtu;
-    if (P == 1) {
-      uint2 v = *reinterpret_cast<const uint2*>(row);
+    for (int r = 0; r < 8; ++r) {
+      const uint2 v = lds_u64(reg0 + r * kCtu);
       s = __dp4a(v.x, 0x01010101u, s);
       s = __dp4a(v.y, 0x01010101u, s);
-    } else {
-#pragma unroll
-      for (int k = 0; k < P / 2; ++k) {
-        uint4 v = *reinterpret_cast<const uint4*>(row + 16 * k);
+    }
+  } else {
+    const int rows = 8 * pool, chunks = pool >> 1;  // 16 rows x 16 B or 32 rows x 32 B
+#pragma unroll 4
+    for (int r = 0; r < rows; ++r) {
+      for (int k = 0; k < chunks; ++k) {
+        const uint4 v = lds_u128(reg0 + r * kCtu + 16 * k);
         s = __dp4a(v.x, 0x01010101u, s);
         s = __dp4a(v.y, 0x01010101u, s);
         s = __dp4a(v.z, 0x01010101u, s);
@@ -77,180 +104,210 @@ __device__ __forceinline__ uint32_t region_sum(const uint8_t* __restrict__ reg0)
 
 // Pooled integer sums of one conv1 patch: 4x4 pooled samples = (4P) x (4P) pixels at p0; s[ky*4 + kx].
 template <int P>
-__device__ __forceinline__ void load_patch(const uint8_t* __restrict__ p0, uint32_t (&s)[16]) {
+__device__ __forceinline__ void load_patch_p(uint32_t p0, int (&s)[16]) {
 #pragma unroll
   for (int ky = 0; ky < 4; ++ky) {
     if (P == 1) {
-      const uint32_t w = *reinterpret_cast<const uint32_t*>(p0 + ky * kCtu);
-      s[ky * 4 + 0] = w & 0xffu;
-      s[ky * 4 + 1] = (w >> 8) & 0xffu;
-      s[ky * 4 + 2] = (w >> 16) & 0xffu;
-      s[ky * 4 + 3] = w >> 24;
+      const uint32_t w = lds_u32(p0 + ky * kCtu);
+      s[ky * 4 + 0] = int(w & 0xffu);
+      s[ky * 4 + 1] = int((w >> 8) & 0xffu);
+      s[ky * 4 + 2] = int((w >> 16) & 0xffu);
+      s[ky * 4 + 3] = int(w >> 24);
     } else if (P == 2) {
-      const uint2 a = *reinterpret_cast<const uint2*>(p0 + (2 * ky) * kCtu);
-      const uint2 b = *reinterpret_cast<const uint2*>(p0 + (2 * ky + 1) * kCtu);
-      s[ky * 4 + 0] = __dp4a(b.x, 0x00000101u, __dp4a(a.x, 0x00000101u, 0u));
-      s[ky * 4 + 1] = __dp4a(b.x, 0x01010000u, __dp4a(a.x, 0x01010000u, 0u));
-      s[ky * 4 + 2] = __dp4a(b.y, 0x00000101u, __dp4a(a.y, 0x00000101u, 0u));
-      s[ky * 4 + 3] = __dp4a(b.y, 0x01010000u, __dp4a(a.y, 0x01010000u, 0u));
+      const uint2 a = lds_u64(p0 + (2 * ky) * kCtu);
+      const uint2 b = lds_u64(p0 + (2 * ky + 1) * kCtu);
+      s[ky * 4 + 0] = int(__dp4a(b.x, 0x00000101u, __dp4a(a.x, 0x00000101u, 0u)));
+      s[ky * 4 + 1] = int(__dp4a(b.x, 0x01010000u, __dp4a(a.x, 0x01010000u, 0u)));
+      s[ky * 4 + 2] = int(__dp4a(b.y, 0x00000101u, __dp4a(a.y, 0x00000101u, 0u)));
+      s[ky * 4 + 3] = int(__dp4a(b.y, 0x01010000u, __dp4a(a.y, 0x01010000u, 0u)));
     } else {
       uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
-        const uint4 u = *reinterpret_cast<const uint4*>(p0 + (4 * ky + a) * kCtu);
+        const uint4 u = lds_u128(p0 + (4 * ky + a) * kCtu);
         t0 = __dp4a(u.x, 0x01010101u, t0);
         t1 = __dp4a(u.y, 0x01010101u, t1);
         t2 = __dp4a(u.z, 0x01010101u, t2);
         t3 = __dp4a(u.w, 0x01010101u, t3);
       }
-      s[ky * 4 + 0] = t0, s[ky * 4 + 1] = t1, s[ky * 4 + 2] = t2, s[ky * 4 + 3] = t3;
+      s[ky * 4 + 0] = int(t0), s[ky * 4 + 1] = int(t1), s[ky * 4 + 2] = int(t2), s[ky * 4 + 3] = int(t3);
     }
   }
 }
 
-// The per-lane program shared by the three branches (see file header).
-//   reg0    shared-memory address of the lane's region origin inside its CTU tile
-//   wb      shared-memory weight block of the branch
-//   d       position of the lane inside its quad: conv3 tap (ky = d >> 1, kx = d & 1)
-//   hi_row / lo_row  feature rows of the lane's CTU (global memory)
-//   c2_off  offset of the lane's 24 conv2 features, c3_off offset of its quad's 32 conv3 features
-template <int P>
-__device__ __forceinline__ void lane_program(const uint8_t* __restrict__ reg0, const uint32_t wb, float cst,
-                                             float fscale, int d, __half* __restrict__ hi_row,
-                                             __half* __restrict__ lo_row, int c2_off, int c3_off, bool valid) {
-  uint32_t rsum = region_sum<P>(reg0);
-  rsum += __shfl_xor_sync(0xffffffffu, rsum, 1);
-  rsum += __shfl_xor_sync(0xffffffffu, rsum, 2);
-  const int wsum = static_cast<int>(rsum);  // integer sum over the 16x16 pooled window (256*P*P pixels)
-
-  float acc2[24];
-  {
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      float4 v = lds128(wb + 4 * (kB2Off + 4 * i));
-      acc2[4 * i] = v.x, acc2[4 * i + 1] = v.y, acc2[4 * i + 2] = v.z, acc2[4 * i + 3] = v.w;
-    }
+__device__ __forceinline__ void load_patch(int pool, uint32_t p0, int (&s)[16]) {
+  if (pool == 1) {
+    load_patch_p<1>(p0, s);
+  } else if (pool == 2) {
+    load_patch_p<2>(p0, s);
+  } else {
+    load_patch_p<4>(p0, s);
   }
+}
+
+struct Region {
+  uint32_t px;         // shared-memory address of the region origin inside its CTU tile
+  __half* hi;          // feature rows of the region's CTU (global memory)
+  __half* lo;
+  bool valid;          // CTU exists (tail groups run with masked stores)
+};
+
+// One warp task: every lane runs the conv stack for its two regions A and B.
+//   pool    1 / 2 / 4 (warp-uniform)       wb  shared-memory byte address of the branch's weight block
+//   d       position of the lane inside its quad: conv3 tap (ky = d >> 1, kx = d & 1)
+//   c2_off  offset of a region's 24 conv2 features, c3_off offset of its quad's 32 conv3 features
+__device__ __noinline__ void warp_task(const int pool, const uint32_t wb, const float cst, const float fscale, const int d,
+                                       const Region ra, const Region rb, const int c2_off_a, const int c2_off_b,
+                                       const int c3_off_a, const int c3_off_b) {
+  // ---- mean-removal window sums (integer, over the quad's 16x16 pooled samples)
+  uint32_t sa = region_sum(pool, ra.px), sb = region_sum(pool, rb.px);
+  sa += __shfl_xor_sync(0xffffffffu, sa, 1);
+  sb += __shfl_xor_sync(0xffffffffu, sb, 1);
+  sa += __shfl_xor_sync(0xffffffffu, sa, 2);
+  sb += __shfl_xor_sync(0xffffffffu, sb, 2);
+  const int wsum_a = int(sa), wsum_b = int(sb);
+
+  // ---- conv1 (4x4/s4, 1->16) feeding conv2 (2x2/s2, 16->24) patch by patch
+  float2 acc_a[12], acc_b[12];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    lds_pairs(wb + 4 * (kB2Off + 4 * i), acc_a[2 * i], acc_a[2 * i + 1]);
+    acc_b[2 * i] = acc_a[2 * i], acc_b[2 * i + 1] = acc_a[2 * i + 1];
+  }
+  const int patch_step = 4 * pool;
 #pragma unroll 1
   for (int patch = 0; patch < 4; ++patch) {
-    const int py = patch >> 1, px = patch & 1;
-    uint32_t ps[16];
-    load_patch<P>(reg0 + (4 * P * py) * kCtu + 4 * P * px, ps);
-    float a1[16];
-    {
+    const int poff = ((patch >> 1) * kCtu + (patch & 1)) * patch_step;
+    int ps_a[16], ps_b[16];
+    load_patch(pool, ra.px + poff, ps_a);
+    load_patch(pool, rb.px + poff, ps_b);
+    float2 a1_a[8], a1_b[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float4 v = lds128(wb + 4 * (kB1Off + 4 * i));
-        a1[4 * i] = v.x, a1[4 * i + 1] = v.y, a1[4 * i + 2] = v.z, a1[4 * i + 3] = v.w;
-      }
+    for (int i = 0; i < 4; ++i) {
+      lds_pairs(wb + 4 * (kB1Off + 4 * i), a1_a[2 * i], a1_a[2 * i + 1]);
+      a1_b[2 * i] = a1_a[2 * i], a1_b[2 * i + 1] = a1_a[2 * i + 1];
     }
 #pragma unroll
     for (int t = 0; t < 16; ++t) {
-      const float x = __int2float_rn(static_cast<int>(ps[t]) * 256 - wsum) * cst;
+      const float2 xa = splat(__int2float_rn(ps_a[t] * 256 - wsum_a) * cst);
+      const float2 xb = splat(__int2float_rn(ps_b[t] * 256 - wsum_b) * cst);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float4 v = lds128(wb + 4 * (kW1Off + t * 16 + 4 * i));
-        a1[4 * i] = fmaf(x, v.x, a1[4 * i]);
-        a1[4 * i + 1] = fmaf(x, v.y, a1[4 * i + 1]);
-        a1[4 * i + 2] = fmaf(x, v.z, a1[4 * i + 2]);
-        a1[4 * i + 3] = fmaf(x, v.w, a1[4 * i + 3]);
+        float2 w0, w1;
+        lds_pairs(wb + 4 * (kW1Off + t * 16 + 4 * i), w0, w1);
+        a1_a[2 * i] = __ffma2_rn(xa, w0, a1_a[2 * i]);
+        a1_a[2 * i + 1] = __ffma2_rn(xa, w1, a1_a[2 * i + 1]);
+        a1_b[2 * i] = __ffma2_rn(xb, w0, a1_b[2 * i]);
+        a1_b[2 * i + 1] = __ffma2_rn(xb, w1, a1_b[2 * i + 1]);
       }
     }
+    const uint32_t w2 = wb + 4 * (kW2Off + patch * 16 * 24);
 #pragma unroll
     for (int ci = 0; ci < 16; ++ci) {
-      const float c = leaky(a1[ci]);
-      const uint32_t w = wb + 4 * (kW2Off + (patch * 16 + ci) * 24);
+      const float2 ca = splat(leaky((ci & 1) ? a1_a[ci >> 1].y : a1_a[ci >> 1].x));
+      const float2 cb = splat(leaky((ci & 1) ? a1_b[ci >> 1].y : a1_b[ci >> 1].x));
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
-        float4 v = lds128(w + 16 * i);
-        acc2[4 * i] = fmaf(c, v.x, acc2[4 * i]);
-        acc2[4 * i + 1] = fmaf(c, v.y, acc2[4 * i + 1]);
-        acc2[4 * i + 2] = fmaf(c, v.z, acc2[4 * i + 2]);
-        acc2[4 * i + 3] = fmaf(c, v.w, acc2[4 * i + 3]);
+        float2 w0, w1;
+        lds_pairs(w2 + 4 * (ci * 24 + 4 * i), w0, w1);
+        acc_a[2 * i] = __ffma2_rn(ca, w0, acc_a[2 * i]);
+        acc_a[2 * i + 1] = __ffma2_rn(ca, w1, acc_a[2 * i + 1]);
+        acc_b[2 * i] = __ffma2_rn(cb, w0, acc_b[2 * i]);
+        acc_b[2 * i + 1] = __ffma2_rn(cb, w1, acc_b[2 * i + 1]);
       }
     }
   }
 
-  // conv2 output of this lane: 24 features, stored as hi/lo fp16
+  // ---- conv2 outputs: 24 features per region, stored as fp16 hi/lo
 #pragma unroll
-  for (int i = 0; i < 24; ++i) acc2[i] = leaky(acc2[i]);
-  if (valid) {
+  for (int i = 0; i < 12; ++i) acc_a[i] = leaky2(acc_a[i]), acc_b[i] = leaky2(acc_b[i]);
+  {
     uint32_t hw[12], lw[12];
 #pragma unroll
-    for (int i = 0; i < 12; ++i) {
-      float h0, l0, h1, l1;
-      split_hi_lo(acc2[2 * i], fscale, h0, l0);
-      split_hi_lo(acc2[2 * i + 1], fscale, h1, l1);
-      hw[i] = pack_half2(h0, h1);
-      lw[i] = pack_half2(l0, l1);
+    for (int i = 0; i < 12; ++i) split_pair(acc_a[i], fscale, hw[i], lw[i]);
+    if (ra.valid) {
+      uint4* ph = reinterpret_cast<uint4*>(ra.hi + c2_off_a);
+      uint4* pl = reinterpret_cast<uint4*>(ra.lo + c2_off_a);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        ph[i] = make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
+        pl[i] = make_uint4(lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]);
+      }
     }
-    uint4* ph = reinterpret_cast<uint4*>(hi_row + c2_off);
-    uint4* pl = reinterpret_cast<uint4*>(lo_row + c2_off);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      ph[i] = make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
-      pl[i] = make_uint4(lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]);
-    }
-  }
-
-  // conv3: this lane contributes tap d (24 inputs) to all 32 channels of the quad's output position
-  float part[32];
+    for (int i = 0; i < 12; ++i) split_pair(acc_b[i], fscale, hw[i], lw[i]);
+    if (rb.valid) {
+      uint4* ph = reinterpret_cast<uint4*>(rb.hi + c2_off_b);
+      uint4* pl = reinterpret_cast<uint4*>(rb.lo + c2_off_b);
 #pragma unroll
-  for (int i = 0; i < 32; ++i) part[i] = 0.f;
-  {
-    const uint32_t w3 = wb + 4 * (kW3Off + d * kW3Stride);
-#pragma unroll
-    for (int ci = 0; ci < 24; ++ci) {
-      const float c = acc2[ci];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float4 v = lds128(w3 + 4 * (ci * 32 + 4 * i));
-        part[4 * i] = fmaf(c, v.x, part[4 * i]);
-        part[4 * i + 1] = fmaf(c, v.y, part[4 * i + 1]);
-        part[4 * i + 2] = fmaf(c, v.z, part[4 * i + 2]);
-        part[4 * i + 3] = fmaf(c, v.w, part[4 * i + 3]);
+      for (int i = 0; i < 3; ++i) {
+        ph[i] = make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
+        pl[i] = make_uint4(lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]);
       }
     }
   }
-  // reduce-scatter over the quad: lane d ends with channels [8d, 8d+8)
-  float r16[16];
-  const bool up2 = (d & 2) != 0;
+
+  // ---- conv3 (2x2/s2, 24->32): lane d contributes tap d; rolled over the four 8-channel output groups,
+  // each summed across the quad with two xor-shuffles; lane d keeps group d.
+  float2 res_a[4], res_b[4];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const float send = up2 ? part[i] : part[16 + i];
-    const float keep = up2 ? part[16 + i] : part[i];
-    r16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  float r8[8];
-  const bool up1 = (d & 1) != 0;
+  for (int i = 0; i < 4; ++i) res_a[i] = res_b[i] = make_float2(0.f, 0.f);
+  const uint32_t w3 = wb + 4 * (kW3Off + d * kW3Stride);
+#pragma unroll 1
+  for (int og = 0; og < 4; ++og) {
+    float2 pa[4], pb[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float send = up1 ? r16[i] : r16[8 + i];
-    const float keep = up1 ? r16[8 + i] : r16[i];
-    r8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-  }
-  {
-    const float4 u = lds128(wb + 4 * (kB3Off + 8 * d)), v = lds128(wb + 4 * (kB3Off + 8 * d + 4));
-    r8[0] = leaky(r8[0] + u.x), r8[1] = leaky(r8[1] + u.y), r8[2] = leaky(r8[2] + u.z), r8[3] = leaky(r8[3] + u.w);
-    r8[4] = leaky(r8[4] + v.x), r8[5] = leaky(r8[5] + v.y), r8[6] = leaky(r8[6] + v.z), r8[7] = leaky(r8[7] + v.w);
-  }
-  if (valid) {
-    uint32_t hw[4], lw[4];
+    for (int i = 0; i < 4; ++i) pa[i] = pb[i] = make_float2(0.f, 0.f);
+    const uint32_t wg = w3 + 4 * (og * 24 * 8);
+#pragma unroll
+    for (int ci = 0; ci < 24; ++ci) {
+      const float2 ca = splat((ci & 1) ? acc_a[ci >> 1].y : acc_a[ci >> 1].x);
+      const float2 cb = splat((ci & 1) ? acc_b[ci >> 1].y : acc_b[ci >> 1].x);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float2 w0, w1;
+        lds_pairs(wg + 4 * (ci * 8 + 4 * i), w0, w1);
+        pa[2 * i] = __ffma2_rn(ca, w0, pa[2 * i]);
+        pa[2 * i + 1] = __ffma2_rn(ca, w1, pa[2 * i + 1]);
+        pb[2 * i] = __ffma2_rn(cb, w0, pb[2 * i]);
+        pb[2 * i + 1] = __ffma2_rn(cb, w1, pb[2 * i + 1]);
+      }
+    }
+    const bool mine = (og == d);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      float h0, l0, h1, l1;
-      split_hi_lo(r8[2 * i], fscale, h0, l0);
-      split_hi_lo(r8[2 * i + 1], fscale, h1, l1);
-      hw[i] = pack_half2(h0, h1);
-      lw[i] = pack_half2(l0, l1);
+      float2 va = pa[i], vb = pb[i];
+      va.x += __shfl_xor_sync(0xffffffffu, va.x, 1), va.y += __shfl_xor_sync(0xffffffffu, va.y, 1);
+      vb.x += __shfl_xor_sync(0xffffffffu, vb.x, 1), vb.y += __shfl_xor_sync(0xffffffffu, vb.y, 1);
+      va.x += __shfl_xor_sync(0xffffffffu, va.x, 2), va.y += __shfl_xor_sync(0xffffffffu, va.y, 2);
+      vb.x += __shfl_xor_sync(0xffffffffu, vb.x, 2), vb.y += __shfl_xor_sync(0xffffffffu, vb.y, 2);
+      if (mine) res_a[i] = va, res_b[i] = vb;
     }
-    *reinterpret_cast<uint4*>(hi_row + c3_off + 8 * d) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-    *reinterpret_cast<uint4*>(lo_row + c3_off + 8 * d) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  }
+  {
+    float2 b[4];
+    lds_pairs(wb + 4 * (kB3Off + 8 * d), b[0], b[1]);
+    lds_pairs(wb + 4 * (kB3Off + 8 * d + 4), b[2], b[3]);
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      split_pair(leaky2(make_float2(res_a[i].x + b[i].x, res_a[i].y + b[i].y)), fscale, hw[i], lw[i]);
+    if (ra.valid) {
+      *reinterpret_cast<uint4*>(ra.hi + c3_off_a + 8 * d) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      *reinterpret_cast<uint4*>(ra.lo + c3_off_a + 8 * d) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      split_pair(leaky2(make_float2(res_b[i].x + b[i].x, res_b[i].y + b[i].y)), fscale, hw[i], lw[i]);
+    if (rb.valid) {
+      *reinterpret_cast<uint4*>(rb.hi + c3_off_b + 8 * d) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      *reinterpret_cast<uint4*>(rb.lo + c3_off_b + 8 * d) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
   }
 }
 
 constexpr int kTileBytes = kCtu * kCtu;                       // 4096
-constexpr int kStageBytes = kGroupCtus * kTileBytes;          // 32768
+constexpr int kStageBytes = kGroupCtus * kTileBytes;          // 65536
 constexpr int kWeightBytes = ((kConvFloats * 4 + 127) / 128) * 128;
 constexpr int kConvSmemBytes = kWeightBytes + kConvStages * kStageBytes + 2 * kConvStages * 8 + 128;
 
@@ -320,6 +377,7 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
     // ---------------- compute warps: warp tasks round-robin ----------------
     const int cw = warp - 1;
     const uint32_t wsm_addr = smem_u32(wsm);
+    const int d = lane & 3;
     for (int t = cw;; t += kConvComputeWarps) {
       const int j = t / kGroupTasks, task = t - j * kGroupTasks;
       const int g = blockIdx.x + j * gridDim.x;
@@ -327,38 +385,36 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
       const int stage = j % kConvStages;
       const uint32_t parity = (j / kConvStages) & 1;
       mbar_wait(&full[stage], parity);
-      const uint8_t* tile0 = tiles + stage * kStageBytes;
+      const uint32_t tile0 = smem_u32(tiles + stage * kStageBytes);
       const int ctu0 = g * kGroupCtus;  // index inside this launch
-      if (task < 16) {
-        const int c = task >> 1, half = task & 1;
-        const int q = lane >> 2, d = lane & 3;
-        const int qy = half * 2 + (q >> 2), qx = q & 3;
-        const int ry = 2 * qy + (d >> 1), rx = 2 * qx + (d & 1);
-        const int n = ctu0 + c;
-        const bool valid = n < p.n_ctus;
-        const size_t row = size_t(valid ? n : 0) * kFeat;
-        lane_program<1>(tile0 + c * kTileBytes + (8 * ry) * kCtu + 8 * rx, wsm_addr, p.cst[0], p.feat_scale, d, p.feat_hi + row,
-                        p.feat_lo + row, kOffC2S + (ry * 8 + rx) * 24, kOffC3S + (qy * 4 + qx) * 32, valid);
-      } else if (task < 20) {
-        const int c = 2 * (task - 16) + (lane >> 4);
-        const int l16 = lane & 15, q = l16 >> 2, d = l16 & 3;
-        const int qy = q >> 1, qx = q & 1;
-        const int ry = 2 * qy + (d >> 1), rx = 2 * qx + (d & 1);
-        const int n = ctu0 + c;
-        const bool valid = n < p.n_ctus;
-        const size_t row = size_t(valid ? n : 0) * kFeat;
-        lane_program<2>(tile0 + c * kTileBytes + (16 * ry) * kCtu + 16 * rx, wsm_addr + 4 * kConvBranchFloats, p.cst[1], p.feat_scale,
-                        d, p.feat_hi + row, p.feat_lo + row, kOffC2M + (ry * 4 + rx) * 24, kOffC3M + (qy * 2 + qx) * 32,
-                        valid);
-      } else {
-        const int c = lane >> 2, d = lane & 3;
-        const int ry = d >> 1, rx = d & 1;
-        const int n = ctu0 + c;
-        const bool valid = n < p.n_ctus;
-        const size_t row = size_t(valid ? n : 0) * kFeat;
-        lane_program<4>(tile0 + c * kTileBytes + (32 * ry) * kCtu + 32 * rx, wsm_addr + 8 * kConvBranchFloats, p.cst[2],
-                        p.feat_scale, d, p.feat_hi + row, p.feat_lo + row, kOffC2L + (ry * 2 + rx) * 24, kOffC3L, valid);
+      int pool, br, ca, cb, ry_a, rx_a, ry_b, rx_b, c2a, c2b, c3a, c3b;
+      if (task < 16) {            // S: one CTU; regions A / B = upper / lower half
+        const int q = lane >> 2, qy = q >> 2, qx = q & 3;
+        pool = 1, br = 0, ca = cb = task;
+        ry_a = 2 * qy + (d >> 1), ry_b = ry_a + 4, rx_a = rx_b = 2 * qx + (d & 1);
+        c2a = kOffC2S + (ry_a * 8 + rx_a) * 24, c2b = kOffC2S + (ry_b * 8 + rx_b) * 24;
+        c3a = kOffC3S + (qy * 4 + qx) * 32, c3b = kOffC3S + ((qy + 2) * 4 + qx) * 32;
+      } else if (task < 20) {     // M: four CTUs; regions A / B in CTUs two apart
+        const int l16 = lane & 15, q = l16 >> 2, qy = q >> 1, qx = q & 1;
+        pool = 2, br = 1, ca = 4 * (task - 16) + (lane >> 4), cb = ca + 2;
+        ry_a = ry_b = 2 * qy + (d >> 1), rx_a = rx_b = 2 * qx + (d & 1);
+        c2a = c2b = kOffC2M + (ry_a * 4 + rx_a) * 24;
+        c3a = c3b = kOffC3M + (qy * 2 + qx) * 32;
+      } else {                    // L: sixteen CTUs; regions A / B in CTUs eight apart
+        pool = 4, br = 2, ca = lane >> 2, cb = ca + 8;
+        ry_a = ry_b = d >> 1, rx_a = rx_b = d & 1;
+        c2a = c2b = kOffC2L + (ry_a * 2 + rx_a) * 24;
+        c3a = c3b = kOffC3L;
       }
+      const int rpx = 8 * pool;   // region edge in pixels
+      Region ra, rb;
+      ra.valid = (ctu0 + ca) < p.n_ctus, rb.valid = (ctu0 + cb) < p.n_ctus;
+      const size_t row_a = size_t(ra.valid ? ctu0 + ca : 0) * kFeat, row_b = size_t(rb.valid ? ctu0 + cb : 0) * kFeat;
+      ra.px = tile0 + ca * kTileBytes + (rpx * ry_a) * kCtu + rpx * rx_a;
+      rb.px = tile0 + cb * kTileBytes + (rpx * ry_b) * kCtu + rpx * rx_b;
+      ra.hi = p.feat_hi + row_a, ra.lo = p.feat_lo + row_a;
+      rb.hi = p.feat_hi + row_b, rb.lo = p.feat_lo + row_b;
+      warp_task(pool, wsm_addr + 4 * br * kConvBranchFloats, p.cst[br], p.feat_scale, d, ra, rb, c2a, c2b, c3a, c3b);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[stage]);
     }

@@ -79,9 +79,9 @@ __global__ void __launch_bounds__(256) fc1_simt_kernel(const __half* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
-// HEADS: one CTA = 32 CTUs of one head.  Thread j < N2 owns FC2 output column j for all 32 CTUs
-// (weights streamed once through registers, activations broadcast from shared memory), then the
-// 32 x N3 FC3 dot products are spread over the block.
+// HEADS: one CTA = 32 CTUs of one head.  FC2 runs on 4-column x 8-CTU register tiles (weights streamed
+// once through registers, activations broadcast from shared memory), then the 32 x N3 FC3 dot products
+// are spread over the block.
 constexpr int kHT = 32;  // CTUs per CTA
 
 template <int N1, int N2, int N3, int OUT_OFF, int COL_OFF>
@@ -102,26 +102,37 @@ __device__ __forceinline__ void heads_body(const HeadsLaunch& p, const HeadWeigh
     a1s[(4 * k4 + 3) * kHT + c] = v.w;
   }
   __syncthreads();
-  if (tid < N2) {
-    float acc[kHT];
-    const float init = fmaf(p.q, w.w2q[tid], w.b2[tid]);
+  // FC2: thread = 4 output columns x 8 CTUs (register tile): per k one 128-bit weight load (coalesced
+  // across threads) and two broadcast 128-bit activation loads feed 32 FMAs.
+  constexpr int CG = N2 / 4;                      // column groups
+  if (tid < CG * 4) {
+    const int cg = tid % CG, rg = tid / CG;
+    float acc[4][8];
+    {
+      const float4 bq = __ldg(reinterpret_cast<const float4*>(w.w2q) + cg), bb = __ldg(reinterpret_cast<const float4*>(w.b2) + cg);
+      const float init[4] = {fmaf(p.q, bq.x, bb.x), fmaf(p.q, bq.y, bb.y), fmaf(p.q, bq.z, bb.z), fmaf(p.q, bq.w, bb.w)};
 #pragma unroll
-    for (int c = 0; c < kHT; ++c) acc[c] = init;
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = init[i];
+    }
+    const float4* wp = reinterpret_cast<const float4*>(w.w2) + cg;
 #pragma unroll 4
     for (int k = 0; k < N1; ++k) {
-      const float wv = __ldg(w.w2 + k * N2 + tid);
-      const float4* a = reinterpret_cast<const float4*>(a1s + k * kHT);
+      const float4 wv = __ldg(wp + k * CG);
+      const float4 a0 = *reinterpret_cast<const float4*>(a1s + k * kHT + 8 * rg);
+      const float4 a1 = *reinterpret_cast<const float4*>(a1s + k * kHT + 8 * rg + 4);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float wq[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
-      for (int c4 = 0; c4 < kHT / 4; ++c4) {
-        const float4 v = a[c4];
-        acc[4 * c4] = fmaf(v.x, wv, acc[4 * c4]);
-        acc[4 * c4 + 1] = fmaf(v.y, wv, acc[4 * c4 + 1]);
-        acc[4 * c4 + 2] = fmaf(v.z, wv, acc[4 * c4 + 2]);
-        acc[4 * c4 + 3] = fmaf(v.w, wv, acc[4 * c4 + 3]);
-      }
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[j], wq[i], acc[i][j]);
     }
 #pragma unroll
-    for (int c = 0; c < kHT; ++c) a2s[tid * (kHT + 1) + c] = leaky(acc[c]);
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a2s[(4 * cg + i) * (kHT + 1) + 8 * rg + j] = leaky(acc[i][j]);
   }
   __syncthreads();
   for (int i = tid; i < kHT * N3; i += NT) {

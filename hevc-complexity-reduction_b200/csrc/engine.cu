@@ -6,7 +6,7 @@
 //   CONV kernel (TMA tiles) -> features fp16 hi/lo [chunk][2688]  (scratch, chunk = 18944 CTUs)
 //   FC1 kernel -> [chunk][448] fp32 -> HEADS kernel -> raw probabilities + gate flags
 //   GATE kernel over the slab -> D2H of 84 B/CTU into the caller's buffer (its frame range = the "gather")
-// Slabs are double-buffered so copies overlap kernels.  With n_gpus > 1 one host thread per device
+// Slabs (~16 MB of luma) rotate through three buffers so copies overlap kernels.  With n_gpus > 1 one host thread per device
 // runs the same pipeline on a contiguous frame range (video_to_cu_depth.py:88 loop, sharded).
 #include <fcntl.h>
 #include <sys/mman.h>
@@ -79,16 +79,17 @@ struct DeviceCtx {
   size_t flags_cap = 0;
   cudaEvent_t ev_last = nullptr;  // end of the previous device call (scratch reuse across streams)
   // staging for the host path
-  static constexpr int kSlabs = 2;
-  uint8_t* d_slab[kSlabs] = {nullptr, nullptr};
-  float* d_prob[kSlabs] = {nullptr, nullptr};
-  uint8_t* h_stage[kSlabs] = {nullptr, nullptr};
-  float* h_prob[kSlabs] = {nullptr, nullptr};
+  static constexpr int kSlabs = 3;
+  uint8_t* d_slab[kSlabs] = {};
+  float* d_prob[kSlabs] = {};
+  uint8_t* h_stage[kSlabs] = {};
+  float* h_prob[kSlabs] = {};
   size_t slab_bytes = 0, slab_prob_floats = 0, stage_bytes = 0, hprob_floats = 0;
-  cudaEvent_t ev_h2d[kSlabs] = {nullptr, nullptr}, ev_comp[kSlabs] = {nullptr, nullptr}, ev_d2h[kSlabs] = {nullptr, nullptr};
+  cudaEvent_t ev_h2d[kSlabs] = {}, ev_comp[kSlabs] = {}, ev_d2h[kSlabs] = {};
   // profiling
   bool profiling = false;
   std::vector<ProfEvent> prof;
+  std::vector<cudaEvent_t> ev_pool;  // timing events are recycled: creating them per launch costs more than the kernels
   double prof_ms[ETHCNN_N_STAGES] = {0, 0, 0, 0};
   int64_t prof_launches[ETHCNN_N_STAGES] = {0, 0, 0, 0};
   int last_used_tma = 0;
@@ -255,8 +256,7 @@ struct StageTimer {
   StageTimer(DeviceCtx& ctx, cudaStream_t stream, int st) : c(ctx), s(stream), stage(st), on(ctx.profiling) {
     if (on) {
       ev.stage = st;
-      cudaEventCreate(&ev.a);
-      cudaEventCreate(&ev.b);
+      ev.a = take(), ev.b = take();
       cudaEventRecord(ev.a, s);
     }
   }
@@ -265,6 +265,16 @@ struct StageTimer {
       cudaEventRecord(ev.b, s);
       c.prof.push_back(ev);
     }
+  }
+  cudaEvent_t take() {
+    cudaEvent_t e = nullptr;
+    if (!c.ev_pool.empty()) {
+      e = c.ev_pool.back();
+      c.ev_pool.pop_back();
+    } else {
+      cudaEventCreate(&e);
+    }
+    return e;
   }
 };
 
@@ -431,10 +441,11 @@ int run_host_pipeline(ethcnn_handle* h, DeviceCtx& c, const uint8_t* y, int widt
   const size_t pitch = (size_t(width) + 15) / 16 * 16;
   const size_t dev_frame = pitch * height;  // multiple of 16
   const int ctus_per_frame = ((width + kCtu - 1) / kCtu) * ((height + kCtu - 1) / kCtu);
-  const size_t target = size_t(48) << 20;
+  // slabs of ~16 MB: small enough that the first H2D and the last kernels/D2H (the un-overlapped ends of the
+  // pipeline) are short, large enough to amortise the ~10 launches per slab
+  const size_t target = size_t(16) << 20;
   int slab_frames = int(std::max<size_t>(1, std::min<size_t>(size_t(n_frames), target / dev_frame)));
-  // at least two slabs when there is more than one frame, so the copies overlap the kernels
-  if (n_frames > 1 && slab_frames > (n_frames + 1) / 2) slab_frames = (n_frames + 1) / 2;
+  if (n_frames > 1 && slab_frames > (n_frames + 2) / 3) slab_frames = (n_frames + 2) / 3;
   const bool src_pinned = is_pinned(y);
   const bool dst_pinned = is_pinned(out);
   int rc = ensure_staging(c, dev_frame * slab_frames, size_t(slab_frames) * ctus_per_frame * per_ctu, !src_pinned, !dst_pinned);
@@ -482,8 +493,6 @@ int run_host_pipeline(ethcnn_handle* h, DeviceCtx& c, const uint8_t* y, int widt
     float* dst = dst_pinned ? out + size_t(f0) * ctus_per_frame * per_ctu : c.h_prob[b];
     CUDA_TRY(cudaMemcpyAsync(dst, c.d_prob[b], nfl * 4, cudaMemcpyDeviceToHost, c.s_d2h));
     CUDA_TRY(cudaEventRecord(c.ev_d2h[b], c.s_d2h));
-    // the next H2D into this device slab must not start before these kernels have consumed it
-    CUDA_TRY(cudaStreamWaitEvent(c.s_h2d, c.ev_comp[b], 0));
     pend[b].slab = slab_idx, pend[b].f0 = f0, pend[b].nf = nf;
   }
   for (int b = 0; b < DeviceCtx::kSlabs; ++b)
@@ -558,6 +567,7 @@ void close_device(DeviceCtx& c) {
     if (c.ev_d2h[i]) cudaEventDestroy(c.ev_d2h[i]);
   }
   for (auto& e : c.prof) cudaEventDestroy(e.a), cudaEventDestroy(e.b);
+  for (auto& e : c.ev_pool) cudaEventDestroy(e);
   if (c.ev_last) cudaEventDestroy(c.ev_last);
   if (c.s_compute) cudaStreamDestroy(c.s_compute);
   if (c.s_h2d) cudaStreamDestroy(c.s_h2d);
@@ -772,7 +782,7 @@ int ethcnn_profile_read(ethcnn_handle* h, int stage, double* ms_total, int64_t* 
       CUDA_TRY(cudaEventElapsedTime(&t, e.a, e.b));
       c.prof_ms[e.stage] += t;
       c.prof_launches[e.stage] += 1;
-      cudaEventDestroy(e.a), cudaEventDestroy(e.b);
+      c.ev_pool.push_back(e.a), c.ev_pool.push_back(e.b);
     }
     c.prof.clear();
     ms += c.prof_ms[stage];

@@ -27,16 +27,16 @@ constexpr int kW1Off = 0;        // [16 taps][16 co]
 constexpr int kB1Off = 256;      // [16]
 constexpr int kW2Off = 272;      // [4 patches][16 ci][24 co]
 constexpr int kB2Off = 1808;     // [24]
-constexpr int kW3Off = 1832;     // [4 quad lanes][24 ci][32 co] + 4 floats of padding per quad lane
-constexpr int kW3Stride = 772;
-constexpr int kB3Off = 4920;     // [32]
-constexpr int kConvBranchFloats = 4952;
+constexpr int kW3Off = 1832;     // [4 quad lanes d][4 channel groups og][24 ci][8 co] + 8 floats of padding per d,
+constexpr int kW3Stride = 776;   //   so the four lanes of a quad read disjoint banks
+constexpr int kB3Off = 4936;     // [32]
+constexpr int kConvBranchFloats = 4968;
 constexpr int kConvFloats = 3 * kConvBranchFloats;  // branch order S, M, L
 
 // conv-stage tiling
-constexpr int kGroupCtus = 8;     // CTUs per shared-memory tile group
-constexpr int kGroupTasks = 21;   // 16 S + 4 M + 1 L warp tasks per group
-constexpr int kConvStages = 4;
+constexpr int kGroupCtus = 16;    // CTUs per shared-memory tile group
+constexpr int kGroupTasks = 21;   // 16 S + 4 M + 1 L warp tasks per group (two regions per lane)
+constexpr int kConvStages = 2;
 constexpr int kConvComputeWarps = 11;  // 12 warps per CTA = 3 per SM sub-partition -> 168 registers per thread
 constexpr int kConvThreads = 32 * (1 + kConvComputeWarps);
 

@@ -89,7 +89,10 @@ bool pack_model(const std::map<std::string, BundleTensor>& t, float input_bound,
     memcpy(dst + kB1Off, b1->data.data(), 16 * 4);
     memcpy(dst + kW2Off, w2->data.data(), 1536 * 4);  // [ky*2+kx][ci][co]
     memcpy(dst + kB2Off, b2->data.data(), 24 * 4);
-    for (int d = 0; d < 4; ++d) memcpy(dst + kW3Off + d * kW3Stride, w3->data.data() + d * 768, 768 * 4);
+    for (int d = 0; d < 4; ++d)  // [d][og][ci][8] <- TF [ky*2+kx = d][ci][co = 8*og + j]
+      for (int og = 0; og < 4; ++og)
+        for (int ci = 0; ci < 24; ++ci)
+          memcpy(dst + kW3Off + d * kW3Stride + (og * 24 + ci) * 8, w3->data.data() + (d * 24 + ci) * 32 + 8 * og, 8 * 4);
     memcpy(dst + kB3Off, b3->data.data(), 32 * 4);
     // rigorous magnitude bounds (leaky never increases |.|)
     double B1[16], B2[24], B3[32];

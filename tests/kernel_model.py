@@ -7,7 +7,7 @@ mapping in conv_stage.cu must be mirrored here."""
 import numpy as np
 
 kOffC3S, kOffC3M, kOffC3L, kOffC2S, kOffC2M, kOffC2L = 0, 512, 640, 672, 2208, 2592
-kW1Off, kB1Off, kW2Off, kB2Off, kW3Off, kW3Stride, kB3Off, kBr = 0, 256, 272, 1808, 1832, 772, 4920, 4952
+kW1Off, kB1Off, kW2Off, kB2Off, kW3Off, kW3Stride, kB3Off, kBr = 0, 256, 272, 1808, 1832, 776, 4936, 4968
 F = np.float32
 
 
@@ -37,66 +37,70 @@ def lane_program(tile, oy, ox, P, wb, cst, d):
                 acc2 = (c * wb[o:o + 24] + acc2).astype(F)
         c2 = leaky(acc2)
         part = np.zeros(32, F)
-        for ci in range(24):
-            o = kW3Off + d * kW3Stride + ci * 32
-            part = (c2[ci] * wb[o:o + 32] + part).astype(F)
+        for og in range(4):                                   # rolled over the four 8-channel output groups
+            for ci in range(24):
+                o = kW3Off + d * kW3Stride + (og * 24 + ci) * 8
+                part[8 * og:8 * og + 8] = (c2[ci] * wb[o:o + 8] + part[8 * og:8 * og + 8]).astype(F)
         return c2, part
     return rsum, rest
 
 
 def conv_features_group(tiles, convw, cst3):
-    """tiles: [8,64,64] uint8 (one tile group).  convw: [3,4952] packed conv weights (S, M, L).
-    Returns float32 [8, 2688] features computed task by task exactly like the kernel."""
-    feat = np.full((8, 2688), np.nan, F)
+    """tiles: [16,64,64] uint8 (one tile group).  convw: [3,4968] packed conv weights (S, M, L).
+    Returns float32 [16, 2688] features computed task by task exactly like the kernel: 21 warp tasks,
+    every lane owning two regions (A, B)."""
+    feat = np.full((16, 2688), np.nan, F)
     for task in range(21):
-        lanes = []
+        regs = []   # per lane: [(c, ry, rx, c2_off, c3_off) for A, B], plus d, P, br
         for lane in range(32):
+            d = lane & 3
             if task < 16:
-                c, half = task >> 1, task & 1
-                q, d = lane >> 2, lane & 3
-                qy, qx = half * 2 + (q >> 2), q & 3
-                ry, rx = 2 * qy + (d >> 1), 2 * qx + (d & 1)
-                P, br, oy, ox = 1, 0, 8 * ry, 8 * rx
-                c2_off, c3_off = kOffC2S + (ry * 8 + rx) * 24, kOffC3S + (qy * 4 + qx) * 32
+                q = lane >> 2
+                qy, qx = q >> 2, q & 3
+                ry_a, rx = 2 * qy + (d >> 1), 2 * qx + (d & 1)
+                ry_b = ry_a + 4
+                P, br = 1, 0
+                A = (task, ry_a, rx, kOffC2S + (ry_a * 8 + rx) * 24, kOffC3S + (qy * 4 + qx) * 32)
+                B = (task, ry_b, rx, kOffC2S + (ry_b * 8 + rx) * 24, kOffC3S + ((qy + 2) * 4 + qx) * 32)
             elif task < 20:
-                c = 2 * (task - 16) + (lane >> 4)
                 l16 = lane & 15
-                q, d = l16 >> 2, l16 & 3
+                q = l16 >> 2
                 qy, qx = q >> 1, q & 1
                 ry, rx = 2 * qy + (d >> 1), 2 * qx + (d & 1)
-                P, br, oy, ox = 2, 1, 16 * ry, 16 * rx
-                c2_off, c3_off = kOffC2M + (ry * 4 + rx) * 24, kOffC3M + (qy * 2 + qx) * 32
+                ca = 4 * (task - 16) + (lane >> 4)
+                P, br = 2, 1
+                A = (ca, ry, rx, kOffC2M + (ry * 4 + rx) * 24, kOffC3M + (qy * 2 + qx) * 32)
+                B = (ca + 2,) + A[1:]
             else:
-                c, d = lane >> 2, lane & 3
+                ca = lane >> 2
                 ry, rx = d >> 1, d & 1
-                P, br, oy, ox = 4, 2, 32 * ry, 32 * rx
-                c2_off, c3_off = kOffC2L + (ry * 2 + rx) * 24, kOffC3L
-            rsum, rest = lane_program(tiles[c], oy, ox, P, convw[br], cst3[br], d)
-            lanes.append(dict(c=c, d=d, rsum=rsum, rest=rest, c2_off=c2_off, c3_off=c3_off, wb=convw[br]))
-        # window sum: two xor-shuffles inside the quad
-        r1 = [lanes[l]["rsum"] + lanes[l ^ 1]["rsum"] for l in range(32)]
-        wsum = [r1[l] + r1[l ^ 2] for l in range(32)]
-        parts = []
-        for l in range(32):
-            c2, part = lanes[l]["rest"](wsum[l])
-            feat[lanes[l]["c"], lanes[l]["c2_off"]:lanes[l]["c2_off"] + 24] = c2
-            parts.append(part)
-        # reduce-scatter: lane d ends with channels [8d, 8d+8)
-        r16 = []
-        for l in range(32):
-            up2 = (lanes[l]["d"] & 2) != 0
-            send_from_peer = parts[l ^ 2][16:] if up2 else parts[l ^ 2][:16]   # what the peer sends = the half I keep
-            keep = parts[l][16:] if up2 else parts[l][:16]
-            r16.append((keep + send_from_peer).astype(F))
-        for l in range(32):
-            d = lanes[l]["d"]
-            up1 = (d & 1) != 0
-            peer = r16[l ^ 1][8:] if up1 else r16[l ^ 1][:8]
-            keep = r16[l][8:] if up1 else r16[l][:8]
-            r8 = (keep + peer).astype(F)
-            b3 = lanes[l]["wb"][kB3Off + 8 * d:kB3Off + 8 * d + 8]
-            o = lanes[l]["c3_off"] + 8 * d
-            feat[lanes[l]["c"], o:o + 8] = leaky((r8 + b3).astype(F))
+                P, br = 4, 2
+                A = (ca, ry, rx, kOffC2L + (ry * 2 + rx) * 24, kOffC3L)
+                B = (ca + 8,) + A[1:]
+            regs.append((d, P, br, A, B))
+        for which in (3, 4):     # region A of every lane, then region B: the quad exchanges stay inside one of them
+            lanes = []
+            for lane in range(32):
+                d, P, br = regs[lane][:3]
+                c, ry, rx, c2_off, c3_off = regs[lane][which]
+                rsum, rest = lane_program(tiles[c], 8 * P * ry, 8 * P * rx, P, convw[br], cst3[br], d)
+                lanes.append(dict(c=c, d=d, rsum=rsum, rest=rest, c2_off=c2_off, c3_off=c3_off, wb=convw[br]))
+            r1 = [lanes[l]["rsum"] + lanes[l ^ 1]["rsum"] for l in range(32)]
+            wsum = [r1[l] + r1[l ^ 2] for l in range(32)]
+            parts = []
+            for l in range(32):
+                c2, part = lanes[l]["rest"](wsum[l])
+                feat[lanes[l]["c"], lanes[l]["c2_off"]:lanes[l]["c2_off"] + 24] = c2
+                parts.append(part)
+            # per output group: all-reduce over the quad (xor 1, then xor 2); lane d keeps group d
+            for l in range(32):
+                d = lanes[l]["d"]
+                g = slice(8 * d, 8 * d + 8)
+                s1 = {m: (parts[m][g] + parts[m ^ 1][g]).astype(F) for m in (l, l ^ 2)}
+                r8 = (s1[l] + s1[l ^ 2]).astype(F)
+                b3 = lanes[l]["wb"][kB3Off + 8 * d:kB3Off + 8 * d + 8]
+                o = lanes[l]["c3_off"] + 8 * d
+                feat[lanes[l]["c"], o:o + 8] = leaky((r8 + b3).astype(F))
     return feat
 
 

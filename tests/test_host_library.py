@@ -45,7 +45,7 @@ def test_missing_library_fails_loudly(eb, monkeypatch, tmp_path):
 
 def _pack(eb, prefix, input_bound=1.0):
     lib = eb.load_library()
-    conv = np.zeros(3 * 4952, np.float32)
+    conv = np.zeros(3 * 4968, np.float32)
     w1 = np.zeros((2688, 448), np.float32)
     b1 = np.zeros(448, np.float32)
     hi = np.zeros((448, 2688), np.uint16)
@@ -54,7 +54,7 @@ def _pack(eb, prefix, input_bound=1.0):
     fb = np.zeros(1, np.float32)
     rc = lib.ethcnn_debug_pack_model(prefix.encode(), C.c_float(input_bound), *[C.c_void_p(a.ctypes.data) for a in
                                                                                    (conv, w1, b1, hi, lo, exps, fb)])
-    return rc, conv.reshape(3, 4952), w1, b1, hi, lo, exps, float(fb[0])
+    return rc, conv.reshape(3, 4968), w1, b1, hi, lo, exps, float(fb[0])
 
 
 @pytest.mark.parametrize("which", ["real", "synthetic"])
@@ -78,10 +78,11 @@ def test_cpp_reader_and_packer_match_oracle(eb, tmp_path, which):
         assert np.array_equal(blk[256:272], v(1))
         assert np.array_equal(blk[272:1808], v(2).reshape(-1))
         assert np.array_equal(blk[1808:1832], v(3))
-        w3 = v(4).reshape(4, 768)
-        for d in range(4):
-            assert np.array_equal(blk[1832 + d * 772: 1832 + d * 772 + 768], w3[d])
-        assert np.array_equal(blk[4920:4952], v(5))
+        w3 = v(4).reshape(4, 24, 4, 8)                       # [d][ci][og][8] in the checkpoint
+        for d in range(4):                                   # [d][og][ci][8] (+8 pad) in shared memory
+            got = blk[1832 + d * 776: 1832 + d * 776 + 768].reshape(4, 24, 8)
+            assert np.array_equal(got, w3[d].transpose(1, 0, 2))
+        assert np.array_equal(blk[4936:4968], v(5))
     ref_w1 = np.concatenate([w["h_fc1__%s__w" % h] for h in ("64", "32", "16")], axis=1)
     assert np.array_equal(w1, ref_w1)
     assert np.array_equal(b1, np.concatenate([w["h_fc1__%s__b" % h] for h in ("64", "32", "16")]))

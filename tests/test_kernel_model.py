@@ -12,7 +12,7 @@ from oracle import ethcnn_oracle as eo
 
 def _packed(eb, prefix, bound):
     lib = eb.load_library()
-    conv = np.zeros(3 * 4952, np.float32)
+    conv = np.zeros(3 * 4968, np.float32)
     b1 = np.zeros(448, np.float32)
     hi = np.zeros((448, 2688), np.uint16)
     lo = np.zeros((448, 2688), np.uint16)
@@ -21,7 +21,7 @@ def _packed(eb, prefix, bound):
                                      C.c_void_p(b1.ctypes.data), C.c_void_p(hi.ctypes.data), C.c_void_p(lo.ctypes.data),
                                      C.c_void_p(exps.ctypes.data), None)
     assert rc == 0
-    return conv.reshape(3, 4952), b1, hi, lo, int(exps[0]), int(exps[1])
+    return conv.reshape(3, 4968), b1, hi, lo, int(exps[0]), int(exps[1])
 
 
 @pytest.mark.parametrize("mode", [eo.MODE_AI, eo.MODE_LDP])
@@ -30,7 +30,7 @@ def test_conv_lane_mapping_matches_oracle(eb, tmp_path, mode):
     prefix = str(tmp_path / "m.dat")
     tf_bundle.write_bundle(prefix, w)
     conv, *_ = _packed(eb, prefix, 10.0 if mode == eo.MODE_LDP else 1.0)
-    frame = eo.synth_residue_frame(512, 64, 4) if mode == eo.MODE_LDP else eo.synth_frame(512, 64, 4)
+    frame = eo.synth_residue_frame(1024, 64, 4) if mode == eo.MODE_LDP else eo.synth_frame(1024, 64, 4)
     tiles = eo.frame_to_ctus(frame)
     tiles[7] = eo.known_answer_ctus()[0]
     scale = np.float32(10.0 / 255.0) if mode == eo.MODE_LDP else np.float32(1.0 / 255.0)

@@ -25,7 +25,7 @@ def main():
     if not real:
         tf_bundle.write_bundle(os.path.join(work, assets.AI_MODELS[32]), w)
     out["weights"] = "deployed" if real else "synthetic"
-    W, H, nf, qp = 1920, 1080, 2, 32
+    W, H, nf, qp = 1920, 1080, 1, 32   # one frame = one slab = one chunk, so the scratch holds all of it
     yuv = eo.synth_yuv(W, H, nf, seed0=11)
     n = nf * 510
     ctus = np.concatenate([eo.frame_to_ctus(eo.get_Y_for_one_frame(memoryview(yuv), k, W, H)) for k in range(nf)])
