@@ -117,7 +117,8 @@ __device__ __forceinline__ void heads_body(const HeadsLaunch& p, const HeadWeigh
         for (int j = 0; j < 8; ++j) acc[i][j] = init[i];
     }
     const float4* wp = reinterpret_cast<const float4*>(w.w2) + cg;
-#pragma unroll 4
+    // 16 independent weight loads in flight per thread: the FC2 matrices live in L2, not L1
+#pragma unroll 16
     for (int k = 0; k < N1; ++k) {
       const float4 wv = __ldg(wp + k * CG);
       const float4 a0 = *reinterpret_cast<const float4*>(a1s + k * kHT + 8 * rg);

@@ -267,6 +267,7 @@ struct StageTimer {
     }
   }
   cudaEvent_t take() {
+    if (c.ev_pool.empty()) fold_finished(c);
     cudaEvent_t e = nullptr;
     if (!c.ev_pool.empty()) {
       e = c.ev_pool.back();
@@ -275,6 +276,22 @@ struct StageTimer {
       cudaEventCreate(&e);
     }
     return e;
+  }
+  // Fold event pairs that have already completed into the per-stage totals and recycle their events, so a
+  // long timed region needs only as many events as are in flight (cudaEventCreate costs ~0.1 ms).
+  static void fold_finished(DeviceCtx& c) {
+    size_t done = 0;
+    while (done < c.prof.size() && cudaEventQuery(c.prof[done].b) == cudaSuccess) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, c.prof[done].a, c.prof[done].b) == cudaSuccess) {
+        c.prof_ms[c.prof[done].stage] += t;
+        c.prof_launches[c.prof[done].stage] += 1;
+      }
+      c.ev_pool.push_back(c.prof[done].a), c.ev_pool.push_back(c.prof[done].b);
+      ++done;
+    }
+    cudaGetLastError();  // cudaErrorNotReady from the query is expected
+    c.prof.erase(c.prof.begin(), c.prof.begin() + done);
   }
 };
 
@@ -764,7 +781,17 @@ int ethcnn_set_option(ethcnn_handle* h, int option, int64_t value) {
 int ethcnn_profile_enable(ethcnn_handle* h, int on) {
   if (!h) return fail(ETHCNN_E_ARG, "NULL handle");
   std::lock_guard<std::mutex> lock(h->mu);
-  for (auto& c : h->devs) c->profiling = on != 0;
+  for (auto& c : h->devs) {
+    c->profiling = on != 0;
+    if (on && c->ev_pool.size() < 64) {  // pre-create the timing events outside any timed region
+      CUDA_TRY(cudaSetDevice(c->device));
+      while (c->ev_pool.size() < 64) {
+        cudaEvent_t e = nullptr;
+        CUDA_TRY(cudaEventCreate(&e));
+        c->ev_pool.push_back(e);
+      }
+    }
+  }
   return ETHCNN_OK;
 }
 
