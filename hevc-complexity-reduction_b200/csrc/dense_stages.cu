@@ -210,17 +210,16 @@ cudaError_t launch_fc1_simt(const __half* feat_hi, const __half* feat_lo, float 
   return cudaGetLastError();
 }
 
+constexpr int kHeadsSmem = (256 * kHT + 192 * (kHT + 1)) * 4;  // 58112 B
+
+cudaError_t heads_configure() {  // function attributes are per device: call once on every device
+  return cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadsSmem);
+}
+
 cudaError_t launch_heads(const HeadsLaunch& p, cudaStream_t stream) {
   if (p.n_ctus <= 0) return cudaSuccess;
-  static bool configured = false;
-  constexpr int smem = (256 * kHT + 192 * (kHT + 1)) * 4;  // 58112 B
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
   dim3 grid((p.n_ctus + kHT - 1) / kHT, 3);
-  heads_kernel<<<grid, 192, smem, stream>>>(p);
+  heads_kernel<<<grid, 192, kHeadsSmem, stream>>>(p);
   return cudaGetLastError();
 }
 

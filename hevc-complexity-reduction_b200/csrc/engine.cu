@@ -568,6 +568,7 @@ int open_device(ethcnn_handle* h, int device) {
   CUDA_TRY(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
   CUDA_TRY(conv_features_configure());
   CUDA_TRY(fc1_tc_configure());
+  CUDA_TRY(heads_configure());
   h->devs.push_back(std::move(c));
   return ETHCNN_OK;
 }

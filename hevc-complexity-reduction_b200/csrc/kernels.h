@@ -86,6 +86,7 @@ cudaError_t conv_features_configure();  // one-off cudaFuncSetAttribute calls
 cudaError_t launch_fc1_simt(const __half* feat_hi, const __half* feat_lo, float inv_feat_scale, const float* w1 /*[2688][448]*/,
                             const float* b1, float* fc1_out, int n_ctus, cudaStream_t stream);
 
+cudaError_t heads_configure();
 cudaError_t launch_heads(const HeadsLaunch& p, cudaStream_t stream);
 
 cudaError_t launch_gate(float* prob, const unsigned* flags, float t2, long long n_total, int ctus_per_frame,
