@@ -27,6 +27,7 @@
 
 #include "../../include/ethcnn.h"
 #include "fc1_tc.h"
+#include "fc_fused.h"
 #include "kernels.h"
 #include "model.h"
 #include "tf_bundle.h"
@@ -58,6 +59,13 @@ struct DeviceModel {
   HeadWeights hw[3];
   int feat_exp = 0, w_exp = 0;
   Fc1TcWeights tc;         // tensor maps over w1_hi / w1_lo
+  // fused FC1 + FC2 + FC3 kernel
+  __half* w2_hi[3] = {nullptr, nullptr, nullptr};
+  __half* w2_lo[3] = {nullptr, nullptr, nullptr};
+  float* w3_packed = nullptr;  // [48*1 | 96*4 | 192*16]
+  FusedWeights fused;
+  int a1_exp = 0, w2_exp = 0;
+  std::vector<float> h_b2, h_w2q, h_b3, h_w3q;  // host copies: b2eff / b3eff depend on the call's qp
 };
 
 struct ProfEvent {
@@ -108,7 +116,7 @@ struct ethcnn_handle {
   std::vector<std::unique_ptr<DeviceCtx>> devs;
   std::mutex mu;
   std::atomic<int64_t> launches{0};
-  int fc1_path = 1;
+  int fc1_path = 2;  // 0 = SIMT fp32 FC1 + heads kernel, 1 = tcgen05 FC1 + heads kernel, 2 = fused tcgen05 FC1+FC2+FC3
   size_t chunk_ctus = 148 * 128;
 };
 
@@ -175,6 +183,8 @@ int upload(T** dst, const void* src, size_t bytes) {
 
 void free_model(DeviceModel& m) {
   cudaFree(m.conv), cudaFree(m.w1), cudaFree(m.b1), cudaFree(m.w1_hi), cudaFree(m.w1_lo), cudaFree(m.heads);
+  for (int k = 0; k < 3; ++k) cudaFree(m.w2_hi[k]), cudaFree(m.w2_lo[k]);
+  cudaFree(m.w3_packed);
   m = DeviceModel();
 }
 
@@ -220,6 +230,21 @@ int get_model(ethcnn_handle* h, DeviceCtx& c, int qp, DeviceModel** out) {
   m.w_exp = pm.w_exp;
   const char* terr = nullptr;
   if (!fc1_tc_prepare_weights(m.w1_hi, m.w1_lo, &m.tc, &terr)) return fail(ETHCNN_E_CUDA, std::string("FC1 weight tensor map: ") + terr);
+  std::vector<float> w3p;
+  for (int k = 0; k < 3; ++k) {
+    if ((rc = upload(&m.w2_hi[k], pm.w2_hi[k].data(), pm.w2_hi[k].size() * 2))) return rc;
+    if ((rc = upload(&m.w2_lo[k], pm.w2_lo[k].data(), pm.w2_lo[k].size() * 2))) return rc;
+    w3p.insert(w3p.end(), pm.w3[k].begin(), pm.w3[k].end());
+    m.h_b2.insert(m.h_b2.end(), pm.b2[k].begin(), pm.b2[k].end());
+    m.h_w2q.insert(m.h_w2q.end(), pm.w2q[k].begin(), pm.w2q[k].end());
+    m.h_b3.insert(m.h_b3.end(), pm.b3[k].begin(), pm.b3[k].end());
+    m.h_w3q.insert(m.h_w3q.end(), pm.w3q[k].begin(), pm.w3q[k].end());
+  }
+  if ((rc = upload(&m.w3_packed, w3p.data(), w3p.size() * 4))) return rc;
+  m.a1_exp = pm.a1_exp;
+  m.w2_exp = pm.w2_exp;
+  if (!fc_fused_prepare_weights(m.w1_hi, m.w1_lo, m.w2_hi, m.w2_lo, &m.fused, &terr))
+    return fail(ETHCNN_E_CUDA, std::string("fused FC weight tensor maps: ") + terr);
   auto ins = c.models.emplace(prefix, m);
   *out = &ins.first->second;
   return ETHCNN_OK;
@@ -337,6 +362,25 @@ int run_device(ethcnn_handle* h, DeviceCtx& c, const uint8_t* d_y, int width, in
       ++h->launches;
     }
     float* fc1_dst = fc1_out ? fc1_out + size_t(begin) * kFc1 : c.fc1;
+    if (h->fc1_path == 2) {  // FC1 + FC2 + FC3 in one tcgen05 kernel; a1 never leaves the SM
+      FusedParams fp;
+      const float q = scaled_qp(h->mode, qp);
+      for (int i = 0; i < 336; ++i) fp.b2eff[i] = std::fmaf(q, m->h_w2q[i], m->h_b2[i]);
+      for (int i = 0; i < 21; ++i) fp.b3eff[i] = std::fmaf(q, m->h_w3q[i], m->h_b3[i]);
+      fp.unscale1 = std::ldexp(1.0f, -(m->feat_exp + m->w_exp));
+      fp.a1_scale = std::ldexp(1.0f, m->a1_exp);
+      fp.unscale2 = std::ldexp(1.0f, -(m->a1_exp + m->w2_exp));
+      fp.t1 = h->t1, fp.t2 = h->t2;
+      fp.b1 = m->b1, fp.w3 = m->w3_packed;
+      fp.prob = fc1_out ? nullptr : d_out;
+      fp.fc1_out = fc1_out ? fc1_dst : nullptr;
+      fp.flags = gated ? c.flags : nullptr;
+      fp.n_ctus = n, fp.ctu_begin = int(begin), fp.ctus_per_frame = ctus_per_frame, fp.chunks_per_frame = chunks_per_frame;
+      StageTimer t(c, stream, ETHCNN_STAGE_FC1);
+      CUDA_TRY(launch_fc_fused(c.feat_hi, c.feat_lo, m->fused, fp, c.sm_count, stream));
+      ++h->launches;
+      continue;
+    }
     {
       StageTimer t(c, stream, ETHCNN_STAGE_FC1);
       if (h->fc1_path == 1) {
@@ -569,6 +613,7 @@ int open_device(ethcnn_handle* h, int device) {
   CUDA_TRY(conv_features_configure());
   CUDA_TRY(fc1_tc_configure());
   CUDA_TRY(heads_configure());
+  CUDA_TRY(fc_fused_configure());
   h->devs.push_back(std::move(c));
   return ETHCNN_OK;
 }
@@ -599,7 +644,7 @@ int create_common(const char* model_dir, const char* thr_path, int mode, const s
   std::unique_ptr<ethcnn_handle> h(new ethcnn_handle());
   h->mode = mode;
   h->model_dir = (model_dir && *model_dir) ? model_dir : ".";
-  if (const char* e = getenv("ETHCNN_FC1")) h->fc1_path = (strcmp(e, "simt") == 0) ? 0 : 1;
+  if (const char* e = getenv("ETHCNN_FC1")) h->fc1_path = (strcmp(e, "simt") == 0) ? 0 : (strcmp(e, "tc") == 0 ? 1 : 2);
   if (mode == ETHCNN_MODE_AI) {
     const std::string tp = thr_path ? std::string(thr_path) : h->model_dir + "/Thr_info.txt";
     int rc = read_thresholds(tp, &h->t1, &h->t2);
@@ -767,7 +812,7 @@ int ethcnn_set_option(ethcnn_handle* h, int option, int64_t value) {
   std::lock_guard<std::mutex> lock(h->mu);
   switch (option) {
     case ETHCNN_OPT_FC1_PATH:
-      if (value != 0 && value != 1) return fail(ETHCNN_E_ARG, "FC1 path must be 0 or 1");
+      if (value < 0 || value > 2) return fail(ETHCNN_E_ARG, "FC path must be 0, 1 or 2");
       h->fc1_path = int(value);
       break;
     case ETHCNN_OPT_CHUNK_CTUS:

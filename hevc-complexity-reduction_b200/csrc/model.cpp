@@ -176,6 +176,39 @@ bool pack_model(const std::map<std::string, BundleTensor>& t, float input_bound,
       out->w1_hi[size_t(j) * kFeat + k] = hi;
       out->w1_lo[size_t(j) * kFeat + k] = f32_to_f16_bits(lo);
     }
+
+  // FC2 operands for the fused kernel
+  double a1_bound = 0;
+  for (int j = 0; j < kFc1; ++j) {
+    double s = 0;
+    for (int k = 0; k < kFeat; ++k) s += std::fabs(out->w1[size_t(k) * kFc1 + j]);
+    s = s * feat_bound + std::fabs(out->b1[j]);
+    if (s > a1_bound) a1_bound = s;
+  }
+  out->a1_bound = float(a1_bound);
+  out->a1_exp = pick_exp(float(a1_bound));
+  float w2max = 0.f;
+  for (int h = 0; h < 3; ++h)
+    for (float v : out->w2[h]) {
+      if (!std::isfinite(v)) {
+        *err = "non-finite FC2 weight";
+        return false;
+      }
+      if (std::fabs(v) > w2max) w2max = std::fabs(v);
+    }
+  out->w2_exp = pick_exp(w2max > 0.f ? w2max : 1.f);
+  const float w2s = std::ldexp(1.0f, out->w2_exp);
+  for (int h = 0; h < 3; ++h) {
+    out->w2_hi[h].resize(size_t(n1[h]) * n2[h]);
+    out->w2_lo[h].resize(size_t(n1[h]) * n2[h]);
+    for (int k = 0; k < n1[h]; ++k)
+      for (int j = 0; j < n2[h]; ++j) {
+        const float s = out->w2[h][size_t(k) * n2[h] + j] * w2s;
+        const uint16_t hi = f32_to_f16_bits(s);
+        out->w2_hi[h][size_t(j) * n1[h] + k] = hi;
+        out->w2_lo[h][size_t(j) * n1[h] + k] = f32_to_f16_bits(s - f16_bits_to_f32(hi));
+      }
+  }
   return true;
 }
 

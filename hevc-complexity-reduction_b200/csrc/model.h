@@ -23,6 +23,11 @@ struct PackedModel {
   float feat_bound = 0.f;         // rigorous bound on |feature| for inputs |x| <= input_bound
   // heads: index 0,1,2 = 64,32,16
   std::vector<float> w2[3], w2q[3], b2[3], w3[3], w3q[3], b3[3];
+  // FC2 for the fused tensor-core kernel: per head [n2][n1] fp16 bits of w2^T * 2^w2_exp (K-major) and residual
+  std::vector<uint16_t> w2_hi[3], w2_lo[3];
+  int a1_exp = 0;                 // FC1 activations are re-split as a1 * 2^a1_exp
+  int w2_exp = 0;
+  float a1_bound = 0.f;           // rigorous bound on |a1|
 };
 
 // input_bound: max |x| after scaling and mean removal (1.0 for AI, 10.0 for LDP).

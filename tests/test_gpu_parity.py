@@ -74,11 +74,12 @@ def test_reference_vectors_ldp(eb, ldp_model_dir, golden_dir):
         assert np.abs(fc1 - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
 
 
-@pytest.mark.parametrize("fc1_path", [1, 0])
+@pytest.mark.parametrize("fc1_path", [2, 1, 0])
 @pytest.mark.parametrize("seed", [1, 2])
 def test_synthetic_weights_vs_oracle(eb, tmp_path, fc1_path, seed):
     """Random checkpoints in the reference's 36-tensor layout: a layout/ordering mistake cannot hide behind
-    trained-weight structure.  Both FC1 implementations (tcgen05 and SIMT) are held to the same bar."""
+    trained-weight structure.  All three dense paths (fused tcgen05 FC1+FC2+FC3, tcgen05 FC1 + heads
+    kernel, SIMT FC1 + heads kernel) are held to the same bar."""
     w = eo.random_weights(seed)
     d = str(tmp_path)
     for name in assets.AI_MODELS.values():

@@ -35,7 +35,7 @@ def main():
     p64 = eo.get_prob(yuv, W, H, qp, w, eo.MODE_AI, (0.5, 0.5), dtype=np.float64)
     p32 = eo.get_prob(yuv, W, H, qp, w, eo.MODE_AI, (0.5, 0.5))
     out["oracle_f32_vs_f64_max_dp"] = float(np.abs(p32 - p64).max())
-    for path, name in ((0, "simt"), (1, "tcgen05")):
+    for path, name in ((0, "simt"), (1, "tcgen05"), (2, "fused")):
         try:
             with eb.EthCnn(work, None, eb.MODE_AI, device=0) as net:
                 net.set_option(1, path)
@@ -43,7 +43,7 @@ def main():
                 got = net.predict_yuv_buffer(np.frombuffer(yuv, np.uint8), W, H, qp)
                 dt = time.time() - t
                 feat = net.debug_read_scratch(0, n)
-                fc1 = net.debug_read_scratch(1, n)
+                fc1 = net.debug_read_scratch(1, n) if path != 2 else a1_64.astype(np.float32)  # fused: a1 stays on chip
             r = {
                 "first_call_s": dt,
                 "feat_max_abs_err": float(np.abs(feat - f64).max()),
