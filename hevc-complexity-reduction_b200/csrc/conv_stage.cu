@@ -5,25 +5,28 @@
 //   per branch: conv 4x4/s4 1->16, conv 2x2/s2 16->24, conv 2x2/s2 24->32, leaky(0.2) after each
 //   features = [c3_S | c3_M | c3_L | c2_S | c2_M | c2_L], each NHWC-flattened.
 //
-// Work decomposition.  All three branches have the same shape once the input is pooled: a "region" is an
-// 8x8 block of (pooled) samples = 2x2 conv1 patches = one conv2 output position, and 2x2 neighbouring
-// regions (a "quad", held by 4 adjacent lanes) share one mean-removal window (16x16 pooled samples) and
-// one conv3 output position.
-//   S: pool 1, region  8x8  px, 64 regions per CTU      M: pool 2, 16x16 px, 16 per CTU
-//   L: pool 4, region 32x32 px,  4 regions per CTU
-// Every lane owns TWO regions (A and B) that use the same filter taps, so each weight fetched from shared
-// memory feeds two packed FMAs (fma.rn.f32x2: two output channels at once) -- a broadcast 128-bit LDS
-// costs two shared-memory wavefronts, and at one region per lane the kernel was bound by that pipe and by
-// instruction fetch (round-1 ncu: 52 % LSU wavefronts, 46 % I-cache misses).  A warp task is therefore
-// one CTU (S), four CTUs (M) or sixteen CTUs (L); a group of 16 CTUs is exactly 16 + 4 + 1 = 21 warp
-// tasks of identical cost.  One code body serves the three branches (the pool factor only changes the
-// small integer-sum loaders), conv3 is rolled over its four 8-channel output groups, and the whole hot
-// loop stays inside the 32 KB instruction cache.
+// All three convolutions are non-overlapping, i.e. small GEMMs, and they run on the tensor cores through
+// warp-level mma.sync.m16n8k16 with the accumulator fragment of one layer re-used, in registers, as the
+// A fragment of the next (no shared-memory or shuffle traffic between layers):
+//   * after pooling all branches look alike: a "region" = 8x8 pooled samples = 2x2 conv1 patches = one
+//     conv2 position; a "quad" = 2x2 regions = one 16x16 mean-removal window = one conv3 position.
+//     S: pool 1, 16 quads per CTU; M: pool 2, 4 quads per CTU; L: pool 4, 1 quad per CTU.
+//   * a warp owns 16 quads (two sets A/B of 8, one per lane group g = lane / 4); the 4 lanes d = lane % 4
+//     of a group split every K dimension the way the A fragment wants it:
+//       conv1  rows = (region pair T, patch p), K = 16 taps: lane d supplies taps (ky = d/2 (+2), kx = 2(d%2)+{0,1})
+//       conv2  rows = regions, K = 64 = (patch, channel): the conv1 C fragment (channels 2d,2d+1,8+2d,9+2d) IS the A fragment
+//       conv3  rows = quads (set A rows 0-7, set B rows 8-15), K = 96 = (region, channel): the conv2 C fragments
+//              of the four regions, in natural order, ARE the A fragments.
+//     Weights sit in shared memory pre-arranged as B fragments (one conflict-free 64-bit load per lane).
+//   * precision: every operand is split into fp16 hi + lo (after exact power-of-two scaling) and three MMAs
+//     (hi*hi, hi*lo, lo*hi) accumulate in fp32 -- 2^-22 relative, like the FC stages.  The mean removal is
+//     exact: with s = pooled integer sum and W = integer window sum, (256 s - W) / 32 is split exactly.
+// A warp task is one CTU (S), four CTUs (M) or sixteen CTUs (L); a group of 16 CTUs is 16 + 4 + 1 = 21
+// warp tasks of identical MMA count (312 mma.sync each).  Round-1 history: an FFMA version of this stage
+// reached 39 % of the fp32 peak and was bound by shared-memory wavefronts for the broadcast weights
+// (profiles/r01c_conv_v2.md); mma.sync does the same MACs 7.4x faster per SM (tools/microbench/hmma_rate.cu).
 //
-// Mean removal is exact: with s = pooled integer sum and W = integer sum of the whole window,
-//   pooled - mean = (256*s - W) / (256*pool^2), one rounding when multiplied by scale/(256*pool^2).
-//
-// A persistent CTA (one per SM) keeps the 58 KB of conv weights resident in shared memory and streams
+// A persistent CTA (one per SM) keeps the 58 KB of weight fragments resident in shared memory and streams
 // 16-CTU tile groups through a 2-deep TMA ring (3-D tensor map over (x, y, frame), 64x64x1 box; the zero
 // fill of out-of-bounds rows/columns IS the reference's zero padding, video_to_cu_depth.py:54-57).
 // One producer warp issues TMA, eleven compute warps take warp tasks round-robin.
@@ -35,31 +38,8 @@
 namespace ethcnn {
 namespace {
 
-// 128-bit shared-memory load of four consecutive weights as two channel pairs.  `asm volatile` on
-// purpose: the conv1 filter is invariant across the patch loop and the compiler would otherwise hoist
-// all 64 loads (256 registers).
-__device__ __forceinline__ void lds_pairs(uint32_t addr, float2& p0, float2& p1) {
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(p0.x), "=f"(p0.y), "=f"(p1.x), "=f"(p1.y) : "r"(addr));
-}
-
 __device__ __forceinline__ float leaky(float v) { return fmaxf(0.2f * v, v); }  // Maximum(alpha*x, x), alpha = 0.2
-__device__ __forceinline__ float2 leaky2(float2 v) { return make_float2(leaky(v.x), leaky(v.y)); }
-__device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
 
-__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-
-// (v.x, v.y) * scale -> packed fp16 hi pair and lo pair with hi + lo == v * scale to ~22 bits
-__device__ __forceinline__ void split_pair(float2 v, float scale, uint32_t& hi, uint32_t& lo) {
-  const float sx = v.x * scale, sy = v.y * scale;
-  const __half2 h = __floats2half2_rn(sx, sy);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = pack_half2(sx - __low2float(h), sy - __high2float(h));
-}
-
-// Explicit shared-memory loads of pixels (32-bit shared addresses keep the compiler from emitting generic LD).
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -75,23 +55,47 @@ __device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ float lds_f32(uint32_t addr) { return __uint_as_float(lds_u32(addr)); }
+__device__ __forceinline__ float2 lds_f32x2(uint32_t addr) {
+  const uint2 v = lds_u64(addr);
+  return make_float2(__uint_as_float(v.x), __uint_as_float(v.y));
+}
 
-// Integer sum of a whole region ((8*pool) x (8*pool) pixels at shared address reg0, row pitch 64).
-__device__ __forceinline__ uint32_t region_sum(int pool, uint32_t reg0) {
+// D(16x8, fp32) += A(16x16, fp16) * B(16x8, fp16); fragment layouts as in the PTX ISA.
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], const uint2 b) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+}
+// split-precision product: d += a_hi b_hi + a_hi b_lo + a_lo b_hi
+__device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], const uint2 bh, const uint2 bl) {
+  mma16816(d, ah, bh);
+  mma16816(d, ah, bl);
+  mma16816(d, al, bh);
+}
+
+// (v0, v1) * scale -> packed fp16 hi pair and lo pair with hi + lo == v * scale to ~22 bits
+__device__ __forceinline__ void split2(float v0, float v1, float scale, uint32_t& hi, uint32_t& lo) {
+  const float s0 = v0 * scale, s1 = v1 * scale;
+  const __half2 h = __floats2half2_rn(s0, s1);
+  const __half2 l = __floats2half2_rn(s0 - __low2float(h), s1 - __high2float(h));
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// Integer sum of a quad's pixel block ((16 pool) x (16 pool) pixels at shared address blk, row pitch 64):
+// lane d adds pooled rows d, d+4, d+8, d+12; the caller reduces over the quad.
+__device__ __forceinline__ uint32_t block_rows_sum(int pool, uint32_t blk, int d) {
   uint32_t s = 0;
-  if (pool == 1) {
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const uint2 v = lds_u64(reg0 + r * kCtu);
-      s = __dp4a(v.x, 0x01010101u, s);
-      s = __dp4a(v.y, 0x01010101u, s);
-    }
-  } else {
-    const int rows = 8 * pool, chunks = pool >> 1;  // 16 rows x 16 B or 32 rows x 32 B
-#pragma unroll 4
-    for (int r = 0; r < rows; ++r) {
+  const int chunks = pool;  // 16-byte chunks per pixel row
+#pragma unroll 1
+  for (int r = d; r < 16; r += 4) {
+#pragma unroll 1
+    for (int a = 0; a < pool; ++a) {
+      const uint32_t row = blk + (pool * r + a) * kCtu;
+#pragma unroll 1
       for (int k = 0; k < chunks; ++k) {
-        const uint4 v = lds_u128(reg0 + r * kCtu + 16 * k);
+        const uint4 v = lds_u128(row + 16 * k);
         s = __dp4a(v.x, 0x01010101u, s);
         s = __dp4a(v.y, 0x01010101u, s);
         s = __dp4a(v.z, 0x01010101u, s);
@@ -102,206 +106,196 @@ __device__ __forceinline__ uint32_t region_sum(int pool, uint32_t reg0) {
   return s;
 }
 
-// Pooled integer sums of one conv1 patch: 4x4 pooled samples = (4P) x (4P) pixels at p0; s[ky*4 + kx].
+// conv1 A operand of region pair T of a quad: for patch p, register reg = rx + 2*ki holds the pooled pair
+// (y = 8T + 4(p/2) + d/2 + 2ki, x = 8rx + 4(p%2) + 2(d%2) + {0,1}) as exact fp16 hi/lo of (256 s - W) / 32.
+__device__ __forceinline__ void cvt_pair(int s0, int s1, int wsum, uint32_t& hi, uint32_t& lo) {
+  const float f0 = __int2float_rn(s0 * 256 - wsum) * 0.03125f, f1 = __int2float_rn(s1 * 256 - wsum) * 0.03125f;
+  const __half2 h = __floats2half2_rn(f0, f1);
+  const __half2 l = __floats2half2_rn(f0 - __low2float(h), f1 - __high2float(h));
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 template <int P>
-__device__ __forceinline__ void load_patch_p(uint32_t p0, int (&s)[16]) {
+__device__ __forceinline__ void load_x_p(uint32_t blk, int T, int d, int wsum, uint32_t (&xh)[16], uint32_t (&xl)[16]) {
+  const int ky0 = d >> 1, xs = 2 * (d & 1);
 #pragma unroll
-  for (int ky = 0; ky < 4; ++ky) {
-    if (P == 1) {
-      const uint32_t w = lds_u32(p0 + ky * kCtu);
-      s[ky * 4 + 0] = int(w & 0xffu);
-      s[ky * 4 + 1] = int((w >> 8) & 0xffu);
-      s[ky * 4 + 2] = int((w >> 16) & 0xffu);
-      s[ky * 4 + 3] = int(w >> 24);
-    } else if (P == 2) {
-      const uint2 a = lds_u64(p0 + (2 * ky) * kCtu);
-      const uint2 b = lds_u64(p0 + (2 * ky + 1) * kCtu);
-      s[ky * 4 + 0] = int(__dp4a(b.x, 0x00000101u, __dp4a(a.x, 0x00000101u, 0u)));
-      s[ky * 4 + 1] = int(__dp4a(b.x, 0x01010000u, __dp4a(a.x, 0x01010000u, 0u)));
-      s[ky * 4 + 2] = int(__dp4a(b.y, 0x00000101u, __dp4a(a.y, 0x00000101u, 0u)));
-      s[ky * 4 + 3] = int(__dp4a(b.y, 0x01010000u, __dp4a(a.y, 0x01010000u, 0u)));
-    } else {
-      uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+  for (int ph = 0; ph < 2; ++ph)
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const uint4 u = lds_u128(p0 + (4 * ky + a) * kCtu);
-        t0 = __dp4a(u.x, 0x01010101u, t0);
-        t1 = __dp4a(u.y, 0x01010101u, t1);
-        t2 = __dp4a(u.z, 0x01010101u, t2);
-        t3 = __dp4a(u.w, 0x01010101u, t3);
+    for (int ki = 0; ki < 2; ++ki) {
+      const int y = 8 * T + 4 * ph + ky0 + 2 * ki;
+      if (P == 1) {
+        const uint4 row = lds_u128(blk + y * kCtu);
+        const uint32_t w[4] = {row.x, row.y, row.z, row.w};
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+          for (int rx = 0; rx < 2; ++rx) {
+            const uint32_t hw = (w[2 * rx + pl] >> (8 * xs)) & 0xffffu;
+            cvt_pair(int(hw & 0xffu), int(hw >> 8), wsum, xh[4 * (2 * ph + pl) + rx + 2 * ki], xl[4 * (2 * ph + pl) + rx + 2 * ki]);
+          }
+      } else {
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+          for (int rx = 0; rx < 2; ++rx) {
+            const int x0 = 8 * rx + 4 * pl + xs;
+            uint32_t s0 = 0, s1 = 0;
+            if (P == 2) {
+              const uint32_t a = lds_u32(blk + (2 * y) * kCtu + 2 * x0), b = lds_u32(blk + (2 * y + 1) * kCtu + 2 * x0);
+              s0 = __dp4a(b, 0x00000101u, __dp4a(a, 0x00000101u, 0u));
+              s1 = __dp4a(b, 0x01010000u, __dp4a(a, 0x01010000u, 0u));
+            } else {
+#pragma unroll
+              for (int a = 0; a < 4; ++a) {
+                const uint2 v = lds_u64(blk + (4 * y + a) * kCtu + 4 * x0);
+                s0 = __dp4a(v.x, 0x01010101u, s0);
+                s1 = __dp4a(v.y, 0x01010101u, s1);
+              }
+            }
+            cvt_pair(int(s0), int(s1), wsum, xh[4 * (2 * ph + pl) + rx + 2 * ki], xl[4 * (2 * ph + pl) + rx + 2 * ki]);
+          }
       }
-      s[ky * 4 + 0] = int(t0), s[ky * 4 + 1] = int(t1), s[ky * 4 + 2] = int(t2), s[ky * 4 + 3] = int(t3);
     }
-  }
 }
 
-__device__ __forceinline__ void load_patch(int pool, uint32_t p0, int (&s)[16]) {
+__device__ __forceinline__ void load_x(int pool, uint32_t blk, int T, int d, int wsum, uint32_t (&xh)[16], uint32_t (&xl)[16]) {
   if (pool == 1) {
-    load_patch_p<1>(p0, s);
+    load_x_p<1>(blk, T, d, wsum, xh, xl);
   } else if (pool == 2) {
-    load_patch_p<2>(p0, s);
+    load_x_p<2>(blk, T, d, wsum, xh, xl);
   } else {
-    load_patch_p<4>(p0, s);
+    load_x_p<4>(blk, T, d, wsum, xh, xl);
   }
 }
 
-struct Region {
-  uint32_t px;         // shared-memory address of the region origin inside its CTU tile
-  __half* hi;          // feature rows of the region's CTU (global memory)
+struct QuadSet {        // what a lane needs to know about its quad in set A or B
+  uint32_t blk;         // shared-memory address of the quad's pixel block inside its CTU tile
+  __half* hi;           // feature rows of the quad's CTU (global memory)
   __half* lo;
-  bool valid;          // CTU exists (tail groups run with masked stores)
+  int c2_off;           // offset of the 24 conv2 features of region 0 of the quad
+  int c3_off;           // offset of the quad's 32 conv3 features
+  bool valid;           // CTU exists (tail groups run with masked stores)
 };
 
-// One warp task: every lane runs the conv stack for its two regions A and B.
-//   pool    1 / 2 / 4 (warp-uniform)       wb  shared-memory byte address of the branch's weight block
-//   d       position of the lane inside its quad: conv3 tap (ky = d >> 1, kx = d & 1)
-//   c2_off  offset of a region's 24 conv2 features, c3_off offset of its quad's 32 conv3 features
-__device__ __noinline__ void warp_task(const int pool, const uint32_t wb, const float cst, const float fscale, const int d,
-                                       const Region ra, const Region rb, const int c2_off_a, const int c2_off_b,
-                                       const int c3_off_a, const int c3_off_b) {
-  // ---- mean-removal window sums (integer, over the quad's 16x16 pooled samples)
-  uint32_t sa = region_sum(pool, ra.px), sb = region_sum(pool, rb.px);
-  sa += __shfl_xor_sync(0xffffffffu, sa, 1);
-  sb += __shfl_xor_sync(0xffffffffu, sb, 1);
-  sa += __shfl_xor_sync(0xffffffffu, sa, 2);
-  sb += __shfl_xor_sync(0xffffffffu, sb, 2);
-  const int wsum_a = int(sa), wsum_b = int(sb);
-
-  // ---- conv1 (4x4/s4, 1->16) feeding conv2 (2x2/s2, 16->24) patch by patch
-  float2 acc_a[12], acc_b[12];
+// One warp task: the conv stack for 16 quads (8 per set).
+//   pool   1 / 2 / 4 (warp-uniform)    wb  shared-memory byte address of the branch's weight block
+//   g24    feature distance between vertically adjacent regions (regions per row * 24)
+__device__ __noinline__ void warp_task(const int pool, const uint32_t wb, const float cst, const float fscale, const int lane,
+                                       const QuadSet qa, const QuadSet qb, const int g24) {
+  const int d = lane & 3;
+  const float u1 = lds_f32(wb + 4 * kHdrOff) * cst, u2 = lds_f32(wb + 4 * (kHdrOff + 1));
+  const float u3 = lds_f32(wb + 4 * (kHdrOff + 2)), sc1 = lds_f32(wb + 4 * (kHdrOff + 3));
+  // this lane's output channels: conv1 {2d, 2d+1, 8+2d, 9+2d}; conv2 / conv3 {8 nt + 2d, +1}
+  const float2 b1lo = lds_f32x2(wb + 4 * (kB1Off + 2 * d)), b1hi = lds_f32x2(wb + 4 * (kB1Off + 8 + 2 * d));
+  uint2 f1h[2], f1l[2];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    lds_pairs(wb + 4 * (kB2Off + 4 * i), acc_a[2 * i], acc_a[2 * i + 1]);
-    acc_b[2 * i] = acc_a[2 * i], acc_b[2 * i + 1] = acc_a[2 * i + 1];
+  for (int nt = 0; nt < 2; ++nt) {
+    f1h[nt] = lds_u64(wb + 4 * kF1HiOff + (nt * 32 + lane) * 8);
+    f1l[nt] = lds_u64(wb + 4 * kF1LoOff + (nt * 32 + lane) * 8);
   }
-  const int patch_step = 4 * pool;
+  uint32_t ah[12], al[12], bh[12], bl[12];   // conv3 A operand: conv2 outputs of set A / set B, pair index 3 r + nt
+#pragma unroll
+  for (int i = 0; i < 12; ++i) ah[i] = al[i] = bh[i] = bl[i] = 0u;
+
+  int wsum = 0;
 #pragma unroll 1
-  for (int patch = 0; patch < 4; ++patch) {
-    const int poff = ((patch >> 1) * kCtu + (patch & 1)) * patch_step;
-    int ps_a[16], ps_b[16];
-    load_patch(pool, ra.px + poff, ps_a);
-    load_patch(pool, rb.px + poff, ps_b);
-    float2 a1_a[8], a1_b[8];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      lds_pairs(wb + 4 * (kB1Off + 4 * i), a1_a[2 * i], a1_a[2 * i + 1]);
-      a1_b[2 * i] = a1_a[2 * i], a1_b[2 * i + 1] = a1_a[2 * i + 1];
+  for (int it = 0; it < 4; ++it) {           // (set, region pair T) = (it / 2, it % 2); rolled to keep the code in the I-cache
+    const int st = it >> 1, T = it & 1;
+    const uint32_t blk = st ? qb.blk : qa.blk;
+    __half* const hi = st ? qb.hi : qa.hi;
+    __half* const lo = st ? qb.lo : qa.lo;
+    const int c2_off = st ? qb.c2_off : qa.c2_off;
+    const bool valid = st ? qb.valid : qa.valid;
+    if (T == 0) {
+      uint32_t ws = block_rows_sum(pool, blk, d);
+      ws += __shfl_xor_sync(0xffffffffu, ws, 1);
+      ws += __shfl_xor_sync(0xffffffffu, ws, 2);
+      wsum = int(ws);  // integer sum over the quad's 16x16 pooled window (256 pool^2 pixels)
     }
+    uint32_t xh[16], xl[16];
+    load_x(pool, blk, T, d, wsum, xh, xl);
+    float d2[3][4];
 #pragma unroll
-    for (int t = 0; t < 16; ++t) {
-      const float2 xa = splat(__int2float_rn(ps_a[t] * 256 - wsum_a) * cst);
-      const float2 xb = splat(__int2float_rn(ps_b[t] * 256 - wsum_b) * cst);
+    for (int nt = 0; nt < 3; ++nt) d2[nt][0] = d2[nt][1] = d2[nt][2] = d2[nt][3] = 0.f;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float2 w0, w1;
-        lds_pairs(wb + 4 * (kW1Off + t * 16 + 4 * i), w0, w1);
-        a1_a[2 * i] = __ffma2_rn(xa, w0, a1_a[2 * i]);
-        a1_a[2 * i + 1] = __ffma2_rn(xa, w1, a1_a[2 * i + 1]);
-        a1_b[2 * i] = __ffma2_rn(xb, w0, a1_b[2 * i]);
-        a1_b[2 * i + 1] = __ffma2_rn(xb, w1, a1_b[2 * i + 1]);
+    for (int p = 0; p < 4; ++p) {
+      // conv1 for patch p of regions 2T (row g) and 2T+1 (row g+8)
+      const uint32_t a1h[4] = {xh[4 * p], xh[4 * p + 1], xh[4 * p + 2], xh[4 * p + 3]};
+      const uint32_t a1l[4] = {xl[4 * p], xl[4 * p + 1], xl[4 * p + 2], xl[4 * p + 3]};
+      float d1[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        d1[nt][0] = d1[nt][1] = d1[nt][2] = d1[nt][3] = 0.f;
+        mma3(d1[nt], a1h, a1l, f1h[nt], f1l[nt]);
+      }
+      // bias + leaky + re-split: the C fragments become the conv2 A fragment of k-step p
+      uint32_t a2h[4], a2l[4];
+      split2(leaky(fmaf(d1[0][0], u1, b1lo.x)), leaky(fmaf(d1[0][1], u1, b1lo.y)), sc1, a2h[0], a2l[0]);
+      split2(leaky(fmaf(d1[0][2], u1, b1lo.x)), leaky(fmaf(d1[0][3], u1, b1lo.y)), sc1, a2h[1], a2l[1]);
+      split2(leaky(fmaf(d1[1][0], u1, b1hi.x)), leaky(fmaf(d1[1][1], u1, b1hi.y)), sc1, a2h[2], a2l[2]);
+      split2(leaky(fmaf(d1[1][2], u1, b1hi.x)), leaky(fmaf(d1[1][3], u1, b1hi.y)), sc1, a2h[3], a2l[3]);
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) {
+        const uint2 wh = lds_u64(wb + 4 * kF2HiOff + ((p * 3 + nt) * 32 + lane) * 8);
+        const uint2 wl = lds_u64(wb + 4 * kF2LoOff + ((p * 3 + nt) * 32 + lane) * 8);
+        mma3(d2[nt], a2h, a2l, wh, wl);
       }
     }
-    const uint32_t w2 = wb + 4 * (kW2Off + patch * 16 * 24);
+    // conv2 outputs of regions 2T (c0, c1) and 2T+1 (c2, c3): features + conv3 A operand (pair index 3 r + nt)
 #pragma unroll
-    for (int ci = 0; ci < 16; ++ci) {
-      const float2 ca = splat(leaky((ci & 1) ? a1_a[ci >> 1].y : a1_a[ci >> 1].x));
-      const float2 cb = splat(leaky((ci & 1) ? a1_b[ci >> 1].y : a1_b[ci >> 1].x));
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        float2 w0, w1;
-        lds_pairs(w2 + 4 * (ci * 24 + 4 * i), w0, w1);
-        acc_a[2 * i] = __ffma2_rn(ca, w0, acc_a[2 * i]);
-        acc_a[2 * i + 1] = __ffma2_rn(ca, w1, acc_a[2 * i + 1]);
-        acc_b[2 * i] = __ffma2_rn(cb, w0, acc_b[2 * i]);
-        acc_b[2 * i + 1] = __ffma2_rn(cb, w1, acc_b[2 * i + 1]);
+    for (int nt = 0; nt < 3; ++nt) {
+      const float2 b2 = lds_f32x2(wb + 4 * (kB2Off + 8 * nt + 2 * d));
+      uint32_t h0, l0, h1, l1;
+      split2(leaky(fmaf(d2[nt][0], u2, b2.x)), leaky(fmaf(d2[nt][1], u2, b2.y)), fscale, h0, l0);
+      split2(leaky(fmaf(d2[nt][2], u2, b2.x)), leaky(fmaf(d2[nt][3], u2, b2.y)), fscale, h1, l1);
+      if (valid) {
+        const int o = c2_off + T * g24 + 8 * nt + 2 * d;
+        *reinterpret_cast<uint32_t*>(hi + o) = h0;
+        *reinterpret_cast<uint32_t*>(lo + o) = l0;
+        *reinterpret_cast<uint32_t*>(hi + o + 24) = h1;
+        *reinterpret_cast<uint32_t*>(lo + o + 24) = l1;
       }
-    }
-  }
-
-  // ---- conv2 outputs: 24 features per region, stored as fp16 hi/lo
-#pragma unroll
-  for (int i = 0; i < 12; ++i) acc_a[i] = leaky2(acc_a[i]), acc_b[i] = leaky2(acc_b[i]);
-  {
-    uint32_t hw[12], lw[12];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) split_pair(acc_a[i], fscale, hw[i], lw[i]);
-    if (ra.valid) {
-      uint4* ph = reinterpret_cast<uint4*>(ra.hi + c2_off_a);
-      uint4* pl = reinterpret_cast<uint4*>(ra.lo + c2_off_a);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        ph[i] = make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
-        pl[i] = make_uint4(lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 12; ++i) split_pair(acc_b[i], fscale, hw[i], lw[i]);
-    if (rb.valid) {
-      uint4* ph = reinterpret_cast<uint4*>(rb.hi + c2_off_b);
-      uint4* pl = reinterpret_cast<uint4*>(rb.lo + c2_off_b);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        ph[i] = make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
-        pl[i] = make_uint4(lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]);
+      if (it == 0) {
+        ah[nt] = h0, al[nt] = l0, ah[3 + nt] = h1, al[3 + nt] = l1;
+      } else if (it == 1) {
+        ah[6 + nt] = h0, al[6 + nt] = l0, ah[9 + nt] = h1, al[9 + nt] = l1;
+      } else if (it == 2) {
+        bh[nt] = h0, bl[nt] = l0, bh[3 + nt] = h1, bl[3 + nt] = l1;
+      } else {
+        bh[6 + nt] = h0, bl[6 + nt] = l0, bh[9 + nt] = h1, bl[9 + nt] = l1;
       }
     }
   }
 
-  // ---- conv3 (2x2/s2, 24->32): lane d contributes tap d; rolled over the four 8-channel output groups,
-  // each summed across the quad with two xor-shuffles; lane d keeps group d.
-  float2 res_a[4], res_b[4];
+  // ---- conv3: rows 0-7 = quads of set A, rows 8-15 = quads of set B; K = 96 in natural (region, channel) order
+  float d3[4][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) res_a[i] = res_b[i] = make_float2(0.f, 0.f);
-  const uint32_t w3 = wb + 4 * (kW3Off + d * kW3Stride);
-#pragma unroll 1
-  for (int og = 0; og < 4; ++og) {
-    float2 pa[4], pb[4];
+  for (int nt = 0; nt < 4; ++nt) d3[nt][0] = d3[nt][1] = d3[nt][2] = d3[nt][3] = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) pa[i] = pb[i] = make_float2(0.f, 0.f);
-    const uint32_t wg = w3 + 4 * (og * 24 * 8);
+  for (int j = 0; j < 6; ++j) {
+    const uint32_t a3h[4] = {ah[2 * j], bh[2 * j], ah[2 * j + 1], bh[2 * j + 1]};
+    const uint32_t a3l[4] = {al[2 * j], bl[2 * j], al[2 * j + 1], bl[2 * j + 1]};
 #pragma unroll
-    for (int ci = 0; ci < 24; ++ci) {
-      const float2 ca = splat((ci & 1) ? acc_a[ci >> 1].y : acc_a[ci >> 1].x);
-      const float2 cb = splat((ci & 1) ? acc_b[ci >> 1].y : acc_b[ci >> 1].x);
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        float2 w0, w1;
-        lds_pairs(wg + 4 * (ci * 8 + 4 * i), w0, w1);
-        pa[2 * i] = __ffma2_rn(ca, w0, pa[2 * i]);
-        pa[2 * i + 1] = __ffma2_rn(ca, w1, pa[2 * i + 1]);
-        pb[2 * i] = __ffma2_rn(cb, w0, pb[2 * i]);
-        pb[2 * i + 1] = __ffma2_rn(cb, w1, pb[2 * i + 1]);
-      }
-    }
-    const bool mine = (og == d);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float2 va = pa[i], vb = pb[i];
-      va.x += __shfl_xor_sync(0xffffffffu, va.x, 1), va.y += __shfl_xor_sync(0xffffffffu, va.y, 1);
-      vb.x += __shfl_xor_sync(0xffffffffu, vb.x, 1), vb.y += __shfl_xor_sync(0xffffffffu, vb.y, 1);
-      va.x += __shfl_xor_sync(0xffffffffu, va.x, 2), va.y += __shfl_xor_sync(0xffffffffu, va.y, 2);
-      vb.x += __shfl_xor_sync(0xffffffffu, vb.x, 2), vb.y += __shfl_xor_sync(0xffffffffu, vb.y, 2);
-      if (mine) res_a[i] = va, res_b[i] = vb;
+    for (int nt = 0; nt < 4; ++nt) {
+      const uint2 wh = lds_u64(wb + 4 * kF3HiOff + ((j * 4 + nt) * 32 + lane) * 8);
+      const uint2 wl = lds_u64(wb + 4 * kF3LoOff + ((j * 4 + nt) * 32 + lane) * 8);
+      mma3(d3[nt], a3h, a3l, wh, wl);
     }
   }
-  {
-    float2 b[4];
-    lds_pairs(wb + 4 * (kB3Off + 8 * d), b[0], b[1]);
-    lds_pairs(wb + 4 * (kB3Off + 8 * d + 4), b[2], b[3]);
-    uint32_t hw[4], lw[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      split_pair(leaky2(make_float2(res_a[i].x + b[i].x, res_a[i].y + b[i].y)), fscale, hw[i], lw[i]);
-    if (ra.valid) {
-      *reinterpret_cast<uint4*>(ra.hi + c3_off_a + 8 * d) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-      *reinterpret_cast<uint4*>(ra.lo + c3_off_a + 8 * d) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  for (int nt = 0; nt < 4; ++nt) {
+    const float2 b3 = lds_f32x2(wb + 4 * (kB3Off + 8 * nt + 2 * d));
+    uint32_t h0, l0, h1, l1;
+    split2(leaky(fmaf(d3[nt][0], u3, b3.x)), leaky(fmaf(d3[nt][1], u3, b3.y)), fscale, h0, l0);
+    split2(leaky(fmaf(d3[nt][2], u3, b3.x)), leaky(fmaf(d3[nt][3], u3, b3.y)), fscale, h1, l1);
+    if (qa.valid) {
+      *reinterpret_cast<uint32_t*>(qa.hi + qa.c3_off + 8 * nt + 2 * d) = h0;
+      *reinterpret_cast<uint32_t*>(qa.lo + qa.c3_off + 8 * nt + 2 * d) = l0;
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      split_pair(leaky2(make_float2(res_b[i].x + b[i].x, res_b[i].y + b[i].y)), fscale, hw[i], lw[i]);
-    if (rb.valid) {
-      *reinterpret_cast<uint4*>(rb.hi + c3_off_b + 8 * d) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-      *reinterpret_cast<uint4*>(rb.lo + c3_off_b + 8 * d) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    if (qb.valid) {
+      *reinterpret_cast<uint32_t*>(qb.hi + qb.c3_off + 8 * nt + 2 * d) = h1;
+      *reinterpret_cast<uint32_t*>(qb.lo + qb.c3_off + 8 * nt + 2 * d) = l1;
     }
   }
 }
@@ -377,44 +371,39 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
     // ---------------- compute warps: warp tasks round-robin ----------------
     const int cw = warp - 1;
     const uint32_t wsm_addr = smem_u32(wsm);
-    const int d = lane & 3;
+    const int g = lane >> 2;
     for (int t = cw;; t += kConvComputeWarps) {
       const int j = t / kGroupTasks, task = t - j * kGroupTasks;
-      const int g = blockIdx.x + j * gridDim.x;
-      if (g >= n_groups) break;
+      const int grp = blockIdx.x + j * gridDim.x;
+      if (grp >= n_groups) break;
       const int stage = j % kConvStages;
       const uint32_t parity = (j / kConvStages) & 1;
       mbar_wait(&full[stage], parity);
       const uint32_t tile0 = smem_u32(tiles + stage * kStageBytes);
-      const int ctu0 = g * kGroupCtus;  // index inside this launch
-      int pool, br, ca, cb, ry_a, rx_a, ry_b, rx_b, c2a, c2b, c3a, c3b;
-      if (task < 16) {            // S: one CTU; regions A / B = upper / lower half
-        const int q = lane >> 2, qy = q >> 2, qx = q & 3;
-        pool = 1, br = 0, ca = cb = task;
-        ry_a = 2 * qy + (d >> 1), ry_b = ry_a + 4, rx_a = rx_b = 2 * qx + (d & 1);
-        c2a = kOffC2S + (ry_a * 8 + rx_a) * 24, c2b = kOffC2S + (ry_b * 8 + rx_b) * 24;
-        c3a = kOffC3S + (qy * 4 + qx) * 32, c3b = kOffC3S + ((qy + 2) * 4 + qx) * 32;
-      } else if (task < 20) {     // M: four CTUs; regions A / B in CTUs two apart
-        const int l16 = lane & 15, q = l16 >> 2, qy = q >> 1, qx = q & 1;
-        pool = 2, br = 1, ca = 4 * (task - 16) + (lane >> 4), cb = ca + 2;
-        ry_a = ry_b = 2 * qy + (d >> 1), rx_a = rx_b = 2 * qx + (d & 1);
-        c2a = c2b = kOffC2M + (ry_a * 4 + rx_a) * 24;
-        c3a = c3b = kOffC3M + (qy * 2 + qx) * 32;
-      } else {                    // L: sixteen CTUs; regions A / B in CTUs eight apart
-        pool = 4, br = 2, ca = lane >> 2, cb = ca + 8;
-        ry_a = ry_b = d >> 1, rx_a = rx_b = d & 1;
-        c2a = c2b = kOffC2L + (ry_a * 2 + rx_a) * 24;
-        c3a = c3b = kOffC3L;
+      const int ctu0 = grp * kGroupCtus;  // index inside this launch
+      // lane group g owns quad (qy, qx) of CTU ca (set A) and of CTU cb / quad row qy + 2 (set B)
+      int pool, br, ca, cb, qy_a, qy_b, qx, rg, qg, c2_base, c3_base;
+      if (task < 16) {            // S: one CTU, 16 quads: set A = upper half, set B = lower half
+        pool = 1, br = 0, ca = cb = task, qy_a = g >> 2, qy_b = qy_a + 2, qx = g & 3, rg = 8, qg = 4;
+        c2_base = kOffC2S, c3_base = kOffC3S;
+      } else if (task < 20) {     // M: four CTUs, 4 quads each: sets A / B in CTUs two apart
+        pool = 2, br = 1, ca = 4 * (task - 16) + (g >> 2), cb = ca + 2, qy_a = qy_b = (g & 3) >> 1, qx = g & 1, rg = 4, qg = 2;
+        c2_base = kOffC2M, c3_base = kOffC3M;
+      } else {                    // L: sixteen CTUs, one quad each: sets A / B in CTUs eight apart
+        pool = 4, br = 2, ca = g, cb = g + 8, qy_a = qy_b = 0, qx = 0, rg = 2, qg = 1;
+        c2_base = kOffC2L, c3_base = kOffC3L;
       }
-      const int rpx = 8 * pool;   // region edge in pixels
-      Region ra, rb;
-      ra.valid = (ctu0 + ca) < p.n_ctus, rb.valid = (ctu0 + cb) < p.n_ctus;
-      const size_t row_a = size_t(ra.valid ? ctu0 + ca : 0) * kFeat, row_b = size_t(rb.valid ? ctu0 + cb : 0) * kFeat;
-      ra.px = tile0 + ca * kTileBytes + (rpx * ry_a) * kCtu + rpx * rx_a;
-      rb.px = tile0 + cb * kTileBytes + (rpx * ry_b) * kCtu + rpx * rx_b;
-      ra.hi = p.feat_hi + row_a, ra.lo = p.feat_lo + row_a;
-      rb.hi = p.feat_hi + row_b, rb.lo = p.feat_lo + row_b;
-      warp_task(pool, wsm_addr + 4 * br * kConvBranchFloats, p.cst[br], p.feat_scale, d, ra, rb, c2a, c2b, c3a, c3b);
+      const int bpx = 16 * pool;  // quad block edge in pixels
+      QuadSet qa, qb;
+      qa.valid = (ctu0 + ca) < p.n_ctus, qb.valid = (ctu0 + cb) < p.n_ctus;
+      const size_t row_a = size_t(qa.valid ? ctu0 + ca : 0) * kFeat, row_b = size_t(qb.valid ? ctu0 + cb : 0) * kFeat;
+      qa.blk = tile0 + ca * kTileBytes + (bpx * qy_a) * kCtu + bpx * qx;
+      qb.blk = tile0 + cb * kTileBytes + (bpx * qy_b) * kCtu + bpx * qx;
+      qa.hi = p.feat_hi + row_a, qa.lo = p.feat_lo + row_a;
+      qb.hi = p.feat_hi + row_b, qb.lo = p.feat_lo + row_b;
+      qa.c2_off = c2_base + ((2 * qy_a) * rg + 2 * qx) * 24, qb.c2_off = c2_base + ((2 * qy_b) * rg + 2 * qx) * 24;
+      qa.c3_off = c3_base + (qy_a * qg + qx) * 32, qb.c3_off = c3_base + (qy_b * qg + qx) * 32;
+      warp_task(pool, wsm_addr + 4 * br * kConvBranchFloats, p.cst[br], p.feat_scale, lane, qa, qb, rg * 24);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[stage]);
     }

@@ -868,7 +868,7 @@ int ethcnn_profile_read(ethcnn_handle* h, int stage, double* ms_total, int64_t* 
 }
 
 int ethcnn_debug_pack_model(const char* ckpt_prefix, float input_bound, float* conv, float* w1, float* b1, uint16_t* w1_hi,
-                            uint16_t* w1_lo, int exps[2], float* feat_bound) {
+                            uint16_t* w1_lo, int exps[16], float* feat_bound) {
   if (!ckpt_prefix) return fail(ETHCNN_E_ARG, "NULL argument");
   std::map<std::string, BundleTensor> tensors;
   std::string err;
@@ -881,7 +881,11 @@ int ethcnn_debug_pack_model(const char* ckpt_prefix, float input_bound, float* c
   if (b1) memcpy(b1, pm.b1.data(), pm.b1.size() * 4);
   if (w1_hi) memcpy(w1_hi, pm.w1_hi.data(), pm.w1_hi.size() * 2);
   if (w1_lo) memcpy(w1_lo, pm.w1_lo.data(), pm.w1_lo.size() * 2);
-  if (exps) exps[0] = pm.feat_exp, exps[1] = pm.w_exp;
+  if (exps) {
+    exps[0] = pm.feat_exp, exps[1] = pm.w_exp, exps[2] = pm.a1_exp, exps[3] = pm.w2_exp;
+    for (int br = 0; br < 3; ++br)
+      for (int k = 0; k < 4; ++k) exps[4 + 4 * br + k] = pm.conv_exp[br][k];
+  }
   if (feat_bound) *feat_bound = pm.feat_bound;
   return ETHCNN_OK;
 }

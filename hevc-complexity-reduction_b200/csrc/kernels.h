@@ -22,15 +22,21 @@ constexpr int kSubBatch = 1024;    // video_to_cu_depth.py:64
 // feature offsets inside the 2688-vector (net_CNN.py:150 concat order)
 constexpr int kOffC3S = 0, kOffC3M = 512, kOffC3L = 640, kOffC2S = 672, kOffC2M = 2208, kOffC2L = 2592;
 
-// conv weight block of one branch as laid out in shared memory (floats)
-constexpr int kW1Off = 0;        // [16 taps][16 co]
-constexpr int kB1Off = 256;      // [16]
-constexpr int kW2Off = 272;      // [4 patches][16 ci][24 co]
-constexpr int kB2Off = 1808;     // [24]
-constexpr int kW3Off = 1832;     // [4 quad lanes d][4 channel groups og][24 ci][8 co] + 8 floats of padding per d,
-constexpr int kW3Stride = 776;   //   so the four lanes of a quad read disjoint banks
-constexpr int kB3Off = 4936;     // [32]
-constexpr int kConvBranchFloats = 4968;
+// conv weight block of one branch as laid out in shared memory (32-bit words).  Filters are stored as
+// mma.sync.m16n8k16 B fragments (fp16 hi and lo halves of w * 2^e): fragment (k-step j, n-tile nt) is
+// 32 lanes x 2 registers; lane (g = lane / 4, d = lane % 4) holds {W[16j+2d][8nt+g], W[16j+2d+1][8nt+g]}
+// and {W[16j+2d+8][8nt+g], W[16j+2d+9][8nt+g]} with K in the natural TF order (ky, kx, ci).
+constexpr int kHdrOff = 0;       // floats: [0] 32 * 2^-e1w, [1] 2^-(e_c1 + e2w), [2] 2^-(feat_exp + e3w), [3] 2^e_c1
+constexpr int kB1Off = 16;       // [16] conv1 bias
+constexpr int kB2Off = 32;       // [24] conv2 bias
+constexpr int kB3Off = 56;       // [32] conv3 bias
+constexpr int kF1HiOff = 96;     // conv1:  1 k-step  x 2 n-tiles x 64 words
+constexpr int kF1LoOff = 224;
+constexpr int kF2HiOff = 352;    // conv2:  4 k-steps x 3 n-tiles
+constexpr int kF2LoOff = 1120;
+constexpr int kF3HiOff = 1888;   // conv3:  6 k-steps x 4 n-tiles
+constexpr int kF3LoOff = 3424;
+constexpr int kConvBranchFloats = 4960;
 constexpr int kConvFloats = 3 * kConvBranchFloats;  // branch order S, M, L
 
 // conv-stage tiling

@@ -72,6 +72,13 @@ const BundleTensor* find(const std::map<std::string, BundleTensor>& t, const std
 }  // namespace
 
 bool pack_model(const std::map<std::string, BundleTensor>& t, float input_bound, PackedModel* out, std::string* err) {
+  // power-of-two scales so that fp16 hi parts stay below 2^15 and lo parts stay normal for all but tiny values
+  auto pick_exp = [](float bound) {
+    int e = int(std::floor(std::log2(32768.0 / double(bound))));
+    if (e > 14) e = 14;
+    if (e < -14) e = -14;
+    return e;
+  };
   out->conv.assign(kConvFloats, 0.f);
   const int branch_base[3] = {12, 6, 0};  // S, M, L -> first Variable index (net_CNN.py:126-141)
   float feat_bound = 0.f;
@@ -85,14 +92,8 @@ bool pack_model(const std::map<std::string, BundleTensor>& t, float input_bound,
     const BundleTensor* b3 = find(t, var_name(v + 5), {32}, err);
     if (!w1 || !b1 || !w2 || !b2 || !w3 || !b3) return false;
     float* dst = out->conv.data() + br * kConvBranchFloats;
-    memcpy(dst + kW1Off, w1->data.data(), 256 * 4);   // [ky*4+kx][co]
     memcpy(dst + kB1Off, b1->data.data(), 16 * 4);
-    memcpy(dst + kW2Off, w2->data.data(), 1536 * 4);  // [ky*2+kx][ci][co]
     memcpy(dst + kB2Off, b2->data.data(), 24 * 4);
-    for (int d = 0; d < 4; ++d)  // [d][og][ci][8] <- TF [ky*2+kx = d][ci][co = 8*og + j]
-      for (int og = 0; og < 4; ++og)
-        for (int ci = 0; ci < 24; ++ci)
-          memcpy(dst + kW3Off + d * kW3Stride + (og * 24 + ci) * 8, w3->data.data() + (d * 24 + ci) * 32 + 8 * og, 8 * 4);
     memcpy(dst + kB3Off, b3->data.data(), 32 * 4);
     // rigorous magnitude bounds (leaky never increases |.|)
     double B1[16], B2[24], B3[32];
@@ -113,6 +114,38 @@ bool pack_model(const std::map<std::string, BundleTensor>& t, float input_bound,
       B3[co] = s + std::fabs(b3->data[co]);
       if (B3[co] > feat_bound) feat_bound = float(B3[co]);
     }
+    // filters as mma.sync B fragments, fp16 hi/lo of w * 2^e (K in TF order: w1 [16 taps][16], w2 [64][24], w3 [96][32])
+    auto maxabs = [](const std::vector<float>& v) {
+      float m = 0.f;
+      for (float x : v) m = std::fmax(m, std::fabs(x));
+      return m > 0.f ? m : 1.f;
+    };
+    double b1max = 0;
+    for (int co = 0; co < 16; ++co) b1max = std::fmax(b1max, B1[co]);
+    const int e1w = pick_exp(maxabs(w1->data)), e2w = pick_exp(maxabs(w2->data)), e3w = pick_exp(maxabs(w3->data));
+    const int ec1 = pick_exp(float(b1max));
+    out->conv_exp[br][0] = e1w, out->conv_exp[br][1] = ec1, out->conv_exp[br][2] = e2w, out->conv_exp[br][3] = e3w;
+    auto pack_frags = [&](const std::vector<float>& W, int n_out, int ksteps, int ntiles, int e, int off_hi, int off_lo) {
+      uint16_t* hi = reinterpret_cast<uint16_t*>(dst + off_hi);
+      uint16_t* lo = reinterpret_cast<uint16_t*>(dst + off_lo);
+      const float sc = std::ldexp(1.0f, e);
+      for (int j = 0; j < ksteps; ++j)
+        for (int nt = 0; nt < ntiles; ++nt)
+          for (int lane = 0; lane < 32; ++lane) {
+            const int g = lane >> 2, d = lane & 3;
+            for (int reg = 0; reg < 2; ++reg)
+              for (int el = 0; el < 2; ++el) {
+                const float v = W[size_t(16 * j + 2 * d + 8 * reg + el) * n_out + 8 * nt + g] * sc;
+                const uint16_t h = f32_to_f16_bits(v);
+                const size_t idx = ((size_t(j) * ntiles + nt) * 32 + lane) * 4 + reg * 2 + el;
+                hi[idx] = h;
+                lo[idx] = f32_to_f16_bits(v - f16_bits_to_f32(h));
+              }
+          }
+    };
+    pack_frags(w1->data, 16, 1, 2, e1w, kF1HiOff, kF1LoOff);
+    pack_frags(w2->data, 24, 4, 3, e2w, kF2HiOff, kF2LoOff);
+    pack_frags(w3->data, 32, 6, 4, e3w, kF3HiOff, kF3LoOff);
   }
   out->feat_bound = feat_bound;
 
@@ -156,14 +189,15 @@ bool pack_model(const std::map<std::string, BundleTensor>& t, float input_bound,
     return false;
   }
 
-  // power-of-two scales so that fp16 hi parts stay below 2^15 and lo parts stay normal for all but tiny values
-  auto pick_exp = [](float bound) {
-    int e = int(std::floor(std::log2(32768.0 / double(bound))));
-    if (e > 14) e = 14;
-    if (e < -14) e = -14;
-    return e;
-  };
   out->feat_exp = pick_exp(feat_bound);
+  for (int br = 0; br < 3; ++br) {
+    float* hdr = out->conv.data() + br * kConvBranchFloats + kHdrOff;
+    const int* e = out->conv_exp[br];
+    hdr[0] = std::ldexp(32.0f, -e[0]);                    // conv1: A = (256 s - W) / 32, B = w1 * 2^e1w (times cst at run time)
+    hdr[1] = std::ldexp(1.0f, -(e[1] + e[2]));            // conv2: A = c1 * 2^e_c1, B = w2 * 2^e2w
+    hdr[2] = std::ldexp(1.0f, -(out->feat_exp + e[3]));   // conv3: A = c2 * 2^feat_exp, B = w3 * 2^e3w
+    hdr[3] = std::ldexp(1.0f, e[1]);
+  }
   out->w_exp = pick_exp(wmax > 0.f ? wmax : 1.f);
   const float ws = std::ldexp(1.0f, out->w_exp);
   out->w1_hi.resize(size_t(kFc1) * kFeat);

@@ -18,6 +18,7 @@ struct PackedModel {
   std::vector<float> b1;          // [448]
   std::vector<uint16_t> w1_hi;    // [448][2688] fp16 bits of w1 * 2^w_exp (K-major, for tcgen05)
   std::vector<uint16_t> w1_lo;    // [448][2688] fp16 bits of the residual
+  int conv_exp[3][4] = {};        // per branch: e1w, e_c1, e2w, e3w (power-of-two scales of the conv operands)
   int feat_exp = 0;               // features are stored as value * 2^feat_exp (split into fp16 hi + lo)
   int w_exp = 0;
   float feat_bound = 0.f;         // rigorous bound on |feature| for inputs |x| <= input_bound

@@ -136,12 +136,14 @@ void ethcnn_free_pinned(void* p);
 
 /* Host-side testing hooks (no GPU needed): the checkpoint reader + weight packer and the Thr_info.txt
  * parser, exposed so the CPU test-suite can check them against the oracle.
- *   conv     3 * 4968 floats  (branch S, M, L blocks in the shared-memory layout of csrc/kernels.h)
+ *   conv     3 * 4960 32-bit words (branch S, M, L blocks in the shared-memory layout of csrc/kernels.h:
+ *            header, biases, filters as mma.sync B fragments in fp16 hi/lo)
  *   w1       2688 * 448 floats (heads 64 | 32 | 16 side by side), b1 448 floats
- *   w1_hi/lo 448 * 2688 fp16 bit patterns of w1 * 2^exps[1] (K-major), exps = {feat_exp, w_exp}
+ *   w1_hi/lo 448 * 2688 fp16 bit patterns of w1 * 2^exps[1] (K-major)
+ *   exps     16 ints: feat_exp, w_exp, a1_exp, w2_exp, then per branch (e1w, e_c1, e2w, e3w)
  * Any output pointer may be NULL. */
 int ethcnn_debug_pack_model(const char* ckpt_prefix, float input_bound, float* conv, float* w1, float* b1,
-                            uint16_t* w1_hi, uint16_t* w1_lo, int exps[2], float* feat_bound);
+                            uint16_t* w1_hi, uint16_t* w1_lo, int exps[16], float* feat_bound);
 int ethcnn_debug_read_thresholds(const char* thr_path, float thr[2]);
 uint16_t ethcnn_debug_f32_to_f16(float v);
 /* Device-side testing hook: copy back intermediates of the LAST chunk processed on device 0.

@@ -45,16 +45,16 @@ def test_missing_library_fails_loudly(eb, monkeypatch, tmp_path):
 
 def _pack(eb, prefix, input_bound=1.0):
     lib = eb.load_library()
-    conv = np.zeros(3 * 4968, np.float32)
+    conv = np.zeros(3 * 4960, np.uint32)
     w1 = np.zeros((2688, 448), np.float32)
     b1 = np.zeros(448, np.float32)
     hi = np.zeros((448, 2688), np.uint16)
     lo = np.zeros((448, 2688), np.uint16)
-    exps = np.zeros(2, np.int32)
+    exps = np.zeros(16, np.int32)
     fb = np.zeros(1, np.float32)
     rc = lib.ethcnn_debug_pack_model(prefix.encode(), C.c_float(input_bound), *[C.c_void_p(a.ctypes.data) for a in
                                                                                    (conv, w1, b1, hi, lo, exps, fb)])
-    return rc, conv.reshape(3, 4968), w1, b1, hi, lo, exps, float(fb[0])
+    return rc, conv.reshape(3, 4960), w1, b1, hi, lo, exps, float(fb[0])
 
 
 @pytest.mark.parametrize("which", ["real", "synthetic"])
@@ -70,19 +70,16 @@ def test_cpp_reader_and_packer_match_oracle(eb, tmp_path, which):
         tf_bundle.write_bundle(prefix, w)
     rc, conv, w1, b1, hi, lo, exps, fbound = _pack(eb, prefix)
     assert rc == 0, eb.load_library().ethcnn_last_error()
-    # conv blocks: branch order S, M, L <- Variable_12.., Variable_6.., Variable..
+    # conv blocks: branch order S, M, L <- Variable_12.., Variable_6.., Variable..; the layout (biases + filters
+    # as mma.sync B fragments in fp16 hi/lo) is stated independently in tests/kernel_model.py
+    import kernel_model as km
     for br, base in enumerate((12, 6, 0)):
-        v = lambda i: w["Variable" if base + i == 0 else "Variable_%d" % (base + i)]
-        blk = conv[br]
-        assert np.array_equal(blk[0:256], v(0).reshape(-1))
-        assert np.array_equal(blk[256:272], v(1))
-        assert np.array_equal(blk[272:1808], v(2).reshape(-1))
-        assert np.array_equal(blk[1808:1832], v(3))
-        w3 = v(4).reshape(4, 24, 4, 8)                       # [d][ci][og][8] in the checkpoint
-        for d in range(4):                                   # [d][og][ci][8] (+8 pad) in shared memory
-            got = blk[1832 + d * 776: 1832 + d * 776 + 768].reshape(4, 24, 8)
-            assert np.array_equal(got, w3[d].transpose(1, 0, 2))
-        assert np.array_equal(blk[4936:4968], v(5))
+        want, ex = km.pack_conv_block_reference(w, base, 1.0)
+        assert tuple(exps[4 + 4 * br: 8 + 4 * br]) == ex
+        assert np.array_equal(conv[br][16:], want[16:])                      # everything but the header
+        hdr = conv[br][:4].view(np.float32)
+        assert hdr[0] == np.float32(32.0 * 2.0 ** -ex[0]) and hdr[1] == np.float32(2.0 ** -(ex[1] + ex[2]))
+        assert hdr[2] == np.float32(2.0 ** -(int(exps[0]) + ex[3])) and hdr[3] == np.float32(2.0 ** ex[1])
     ref_w1 = np.concatenate([w["h_fc1__%s__w" % h] for h in ("64", "32", "16")], axis=1)
     assert np.array_equal(w1, ref_w1)
     assert np.array_equal(b1, np.concatenate([w["h_fc1__%s__b" % h] for h in ("64", "32", "16")]))
