@@ -74,9 +74,8 @@ __device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ah)[4], con
   mma16816(d, al, bh);
 }
 
-// (v0, v1) * scale -> packed fp16 hi pair and lo pair with hi + lo == v * scale to ~22 bits
-__device__ __forceinline__ void split2(float v0, float v1, float scale, uint32_t& hi, uint32_t& lo) {
-  const float s0 = v0 * scale, s1 = v1 * scale;
+// (s0, s1) -> packed fp16 hi pair and lo pair with hi + lo == s to ~22 bits
+__device__ __forceinline__ void split2(float s0, float s1, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(s0, s1);
   const __half2 l = __floats2half2_rn(s0 - __low2float(h), s1 - __high2float(h));
   hi = *reinterpret_cast<const uint32_t*>(&h);
@@ -108,8 +107,9 @@ __device__ __forceinline__ uint32_t block_rows_sum(int pool, uint32_t blk, int d
 
 // conv1 A operand of region pair T of a quad: for patch p, register reg = rx + 2*ki holds the pooled pair
 // (y = 8T + 4(p/2) + d/2 + 2ki, x = 8rx + 4(p%2) + 2(d%2) + {0,1}) as exact fp16 hi/lo of (256 s - W) / 32.
-__device__ __forceinline__ void cvt_pair(int s0, int s1, int wsum, uint32_t& hi, uint32_t& lo) {
-  const float f0 = __int2float_rn(s0 * 256 - wsum) * 0.03125f, f1 = __int2float_rn(s1 * 256 - wsum) * 0.03125f;
+__device__ __forceinline__ void cvt_pair(int s0, int s1, float wneg, uint32_t& hi, uint32_t& lo) {
+  // (256 s - W) / 32 = 8 s - W / 32, exact in fp32 (|.| < 2^16 with 5 fractional bits); wneg = -W / 32
+  const float f0 = fmaf(__int2float_rn(s0), 8.0f, wneg), f1 = fmaf(__int2float_rn(s1), 8.0f, wneg);
   const __half2 h = __floats2half2_rn(f0, f1);
   const __half2 l = __floats2half2_rn(f0 - __low2float(h), f1 - __high2float(h));
   hi = *reinterpret_cast<const uint32_t*>(&h);
@@ -117,7 +117,7 @@ __device__ __forceinline__ void cvt_pair(int s0, int s1, int wsum, uint32_t& hi,
 }
 
 template <int P>
-__device__ __forceinline__ void load_x_p(uint32_t blk, int T, int d, int wsum, uint32_t (&xh)[16], uint32_t (&xl)[16]) {
+__device__ __forceinline__ void load_x_p(uint32_t blk, int T, int d, float wsum, uint32_t (&xh)[16], uint32_t (&xl)[16]) {
   const int ky0 = d >> 1, xs = 2 * (d & 1);
 #pragma unroll
   for (int ph = 0; ph < 2; ++ph)
@@ -159,7 +159,7 @@ __device__ __forceinline__ void load_x_p(uint32_t blk, int T, int d, int wsum, u
     }
 }
 
-__device__ __forceinline__ void load_x(int pool, uint32_t blk, int T, int d, int wsum, uint32_t (&xh)[16], uint32_t (&xl)[16]) {
+__device__ __forceinline__ void load_x(int pool, uint32_t blk, int T, int d, float wsum, uint32_t (&xh)[16], uint32_t (&xl)[16]) {
   if (pool == 1) {
     load_x_p<1>(blk, T, d, wsum, xh, xl);
   } else if (pool == 2) {
@@ -184,37 +184,46 @@ struct QuadSet {        // what a lane needs to know about its quad in set A or 
 __device__ __noinline__ void warp_task(const int pool, const uint32_t wb, const float cst, const float fscale, const int lane,
                                        const QuadSet qa, const QuadSet qb, const int g24) {
   const int d = lane & 3;
-  const float u1 = lds_f32(wb + 4 * kHdrOff) * cst, u2 = lds_f32(wb + 4 * (kHdrOff + 1));
-  const float u3 = lds_f32(wb + 4 * (kHdrOff + 2)), sc1 = lds_f32(wb + 4 * (kHdrOff + 3));
+  // leaky(v) * 2^e == leaky(v * 2^e): the power-of-two operand scales are folded into the unscale factors and biases
+  const float sc1 = lds_f32(wb + 4 * (kHdrOff + 3));
+  const float u1 = lds_f32(wb + 4 * kHdrOff) * cst * sc1;
+  const float u2 = lds_f32(wb + 4 * (kHdrOff + 1)) * fscale, u3 = lds_f32(wb + 4 * (kHdrOff + 2)) * fscale;
   // this lane's output channels: conv1 {2d, 2d+1, 8+2d, 9+2d}; conv2 / conv3 {8 nt + 2d, +1}
-  const float2 b1lo = lds_f32x2(wb + 4 * (kB1Off + 2 * d)), b1hi = lds_f32x2(wb + 4 * (kB1Off + 8 + 2 * d));
+  float2 b1lo = lds_f32x2(wb + 4 * (kB1Off + 2 * d)), b1hi = lds_f32x2(wb + 4 * (kB1Off + 8 + 2 * d));
+  b1lo.x *= sc1, b1lo.y *= sc1, b1hi.x *= sc1, b1hi.y *= sc1;
   uint2 f1h[2], f1l[2];
 #pragma unroll
   for (int nt = 0; nt < 2; ++nt) {
     f1h[nt] = lds_u64(wb + 4 * kF1HiOff + (nt * 32 + lane) * 8);
     f1l[nt] = lds_u64(wb + 4 * kF1LoOff + (nt * 32 + lane) * 8);
   }
-  uint32_t ah[12], al[12], bh[12], bl[12];   // conv3 A operand: conv2 outputs of set A / set B, pair index 3 r + nt
+  float d3[4][4];   // conv3 accumulators: rows 0-7 = quads of set A, rows 8-15 = quads of set B
 #pragma unroll
-  for (int i = 0; i < 12; ++i) ah[i] = al[i] = bh[i] = bl[i] = 0u;
+  for (int nt = 0; nt < 4; ++nt) d3[nt][0] = d3[nt][1] = d3[nt][2] = d3[nt][3] = 0.f;
+  uint32_t keep_h[6], keep_l[6];   // set A's conv2 outputs of the current region pair, waiting for set B's
+#pragma unroll
+  for (int i = 0; i < 6; ++i) keep_h[i] = keep_l[i] = 0u;
+  float wneg_a = 0.f, wneg_b = 0.f;
 
-  int wsum = 0;
+  // (region pair T, set st) = (it / 2, it % 2); rolled so that the loop body stays inside the instruction cache
 #pragma unroll 1
-  for (int it = 0; it < 4; ++it) {           // (set, region pair T) = (it / 2, it % 2); rolled to keep the code in the I-cache
-    const int st = it >> 1, T = it & 1;
+  for (int it = 0; it < 4; ++it) {
+    const int T = it >> 1, st = it & 1;
     const uint32_t blk = st ? qb.blk : qa.blk;
     __half* const hi = st ? qb.hi : qa.hi;
     __half* const lo = st ? qb.lo : qa.lo;
     const int c2_off = st ? qb.c2_off : qa.c2_off;
     const bool valid = st ? qb.valid : qa.valid;
     if (T == 0) {
+      // integer sum over the quad's 16x16 pooled window (256 pool^2 pixels), kept as -W/32 (exact)
       uint32_t ws = block_rows_sum(pool, blk, d);
       ws += __shfl_xor_sync(0xffffffffu, ws, 1);
       ws += __shfl_xor_sync(0xffffffffu, ws, 2);
-      wsum = int(ws);  // integer sum over the quad's 16x16 pooled window (256 pool^2 pixels)
+      const float w = -__uint2float_rn(ws) * 0.03125f;
+      if (st) wneg_b = w; else wneg_a = w;
     }
     uint32_t xh[16], xl[16];
-    load_x(pool, blk, T, d, wsum, xh, xl);
+    load_x(pool, blk, T, d, st ? wneg_b : wneg_a, xh, xl);
     float d2[3][4];
 #pragma unroll
     for (int nt = 0; nt < 3; ++nt) d2[nt][0] = d2[nt][1] = d2[nt][2] = d2[nt][3] = 0.f;
@@ -231,10 +240,10 @@ __device__ __noinline__ void warp_task(const int pool, const uint32_t wb, const 
       }
       // bias + leaky + re-split: the C fragments become the conv2 A fragment of k-step p
       uint32_t a2h[4], a2l[4];
-      split2(leaky(fmaf(d1[0][0], u1, b1lo.x)), leaky(fmaf(d1[0][1], u1, b1lo.y)), sc1, a2h[0], a2l[0]);
-      split2(leaky(fmaf(d1[0][2], u1, b1lo.x)), leaky(fmaf(d1[0][3], u1, b1lo.y)), sc1, a2h[1], a2l[1]);
-      split2(leaky(fmaf(d1[1][0], u1, b1hi.x)), leaky(fmaf(d1[1][1], u1, b1hi.y)), sc1, a2h[2], a2l[2]);
-      split2(leaky(fmaf(d1[1][2], u1, b1hi.x)), leaky(fmaf(d1[1][3], u1, b1hi.y)), sc1, a2h[3], a2l[3]);
+      split2(leaky(fmaf(d1[0][0], u1, b1lo.x)), leaky(fmaf(d1[0][1], u1, b1lo.y)), a2h[0], a2l[0]);
+      split2(leaky(fmaf(d1[0][2], u1, b1lo.x)), leaky(fmaf(d1[0][3], u1, b1lo.y)), a2h[1], a2l[1]);
+      split2(leaky(fmaf(d1[1][0], u1, b1hi.x)), leaky(fmaf(d1[1][1], u1, b1hi.y)), a2h[2], a2l[2]);
+      split2(leaky(fmaf(d1[1][2], u1, b1hi.x)), leaky(fmaf(d1[1][3], u1, b1hi.y)), a2h[3], a2l[3]);
 #pragma unroll
       for (int nt = 0; nt < 3; ++nt) {
         const uint2 wh = lds_u64(wb + 4 * kF2HiOff + ((p * 3 + nt) * 32 + lane) * 8);
@@ -242,53 +251,49 @@ __device__ __noinline__ void warp_task(const int pool, const uint32_t wb, const 
         mma3(d2[nt], a2h, a2l, wh, wl);
       }
     }
-    // conv2 outputs of regions 2T (c0, c1) and 2T+1 (c2, c3): features + conv3 A operand (pair index 3 r + nt)
+    // conv2 outputs of regions 2T (c0, c1) and 2T+1 (c2, c3): features (already scaled by 2^feat_exp, hi/lo)
+    uint32_t cur_h[6], cur_l[6];   // pair index 3 (r - 2T) + nt
 #pragma unroll
     for (int nt = 0; nt < 3; ++nt) {
-      const float2 b2 = lds_f32x2(wb + 4 * (kB2Off + 8 * nt + 2 * d));
-      uint32_t h0, l0, h1, l1;
-      split2(leaky(fmaf(d2[nt][0], u2, b2.x)), leaky(fmaf(d2[nt][1], u2, b2.y)), fscale, h0, l0);
-      split2(leaky(fmaf(d2[nt][2], u2, b2.x)), leaky(fmaf(d2[nt][3], u2, b2.y)), fscale, h1, l1);
+      float2 b2 = lds_f32x2(wb + 4 * (kB2Off + 8 * nt + 2 * d));
+      b2.x *= fscale, b2.y *= fscale;
+      split2(leaky(fmaf(d2[nt][0], u2, b2.x)), leaky(fmaf(d2[nt][1], u2, b2.y)), cur_h[nt], cur_l[nt]);
+      split2(leaky(fmaf(d2[nt][2], u2, b2.x)), leaky(fmaf(d2[nt][3], u2, b2.y)), cur_h[3 + nt], cur_l[3 + nt]);
       if (valid) {
         const int o = c2_off + T * g24 + 8 * nt + 2 * d;
-        *reinterpret_cast<uint32_t*>(hi + o) = h0;
-        *reinterpret_cast<uint32_t*>(lo + o) = l0;
-        *reinterpret_cast<uint32_t*>(hi + o + 24) = h1;
-        *reinterpret_cast<uint32_t*>(lo + o + 24) = l1;
+        *reinterpret_cast<uint32_t*>(hi + o) = cur_h[nt];
+        *reinterpret_cast<uint32_t*>(lo + o) = cur_l[nt];
+        *reinterpret_cast<uint32_t*>(hi + o + 24) = cur_h[3 + nt];
+        *reinterpret_cast<uint32_t*>(lo + o + 24) = cur_l[3 + nt];
       }
-      if (it == 0) {
-        ah[nt] = h0, al[nt] = l0, ah[3 + nt] = h1, al[3 + nt] = l1;
-      } else if (it == 1) {
-        ah[6 + nt] = h0, al[6 + nt] = l0, ah[9 + nt] = h1, al[9 + nt] = l1;
-      } else if (it == 2) {
-        bh[nt] = h0, bl[nt] = l0, bh[3 + nt] = h1, bl[3 + nt] = l1;
-      } else {
-        bh[6 + nt] = h0, bl[6 + nt] = l0, bh[9 + nt] = h1, bl[9 + nt] = l1;
+    }
+    if (st == 0) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) keep_h[i] = cur_h[i], keep_l[i] = cur_l[i];
+    } else {
+      // conv3 k-steps 3T .. 3T+2: K = 96 in natural (region, channel) order, regions 2T and 2T+1 of both sets
+#pragma unroll
+      for (int jj = 0; jj < 3; ++jj) {
+        const uint32_t a3h[4] = {keep_h[2 * jj], cur_h[2 * jj], keep_h[2 * jj + 1], cur_h[2 * jj + 1]};
+        const uint32_t a3l[4] = {keep_l[2 * jj], cur_l[2 * jj], keep_l[2 * jj + 1], cur_l[2 * jj + 1]};
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const uint32_t fo = (((3 * T + jj) * 4 + nt) * 32 + lane) * 8;
+          const uint2 wh = lds_u64(wb + 4 * kF3HiOff + fo);
+          const uint2 wl = lds_u64(wb + 4 * kF3LoOff + fo);
+          mma3(d3[nt], a3h, a3l, wh, wl);
+        }
       }
     }
   }
 
-  // ---- conv3: rows 0-7 = quads of set A, rows 8-15 = quads of set B; K = 96 in natural (region, channel) order
-  float d3[4][4];
-#pragma unroll
-  for (int nt = 0; nt < 4; ++nt) d3[nt][0] = d3[nt][1] = d3[nt][2] = d3[nt][3] = 0.f;
-#pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    const uint32_t a3h[4] = {ah[2 * j], bh[2 * j], ah[2 * j + 1], bh[2 * j + 1]};
-    const uint32_t a3l[4] = {al[2 * j], bl[2 * j], al[2 * j + 1], bl[2 * j + 1]};
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const uint2 wh = lds_u64(wb + 4 * kF3HiOff + ((j * 4 + nt) * 32 + lane) * 8);
-      const uint2 wl = lds_u64(wb + 4 * kF3LoOff + ((j * 4 + nt) * 32 + lane) * 8);
-      mma3(d3[nt], a3h, a3l, wh, wl);
-    }
-  }
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
-    const float2 b3 = lds_f32x2(wb + 4 * (kB3Off + 8 * nt + 2 * d));
+    float2 b3 = lds_f32x2(wb + 4 * (kB3Off + 8 * nt + 2 * d));
+    b3.x *= fscale, b3.y *= fscale;
     uint32_t h0, l0, h1, l1;
-    split2(leaky(fmaf(d3[nt][0], u3, b3.x)), leaky(fmaf(d3[nt][1], u3, b3.y)), fscale, h0, l0);
-    split2(leaky(fmaf(d3[nt][2], u3, b3.x)), leaky(fmaf(d3[nt][3], u3, b3.y)), fscale, h1, l1);
+    split2(leaky(fmaf(d3[nt][0], u3, b3.x)), leaky(fmaf(d3[nt][1], u3, b3.y)), h0, l0);
+    split2(leaky(fmaf(d3[nt][2], u3, b3.x)), leaky(fmaf(d3[nt][3], u3, b3.y)), h1, l1);
     if (qa.valid) {
       *reinterpret_cast<uint32_t*>(qa.hi + qa.c3_off + 8 * nt + 2 * d) = h0;
       *reinterpret_cast<uint32_t*>(qa.lo + qa.c3_off + 8 * nt + 2 * d) = l0;

@@ -43,7 +43,10 @@ constexpr int kConvFloats = 3 * kConvBranchFloats;  // branch order S, M, L
 constexpr int kGroupCtus = 16;    // CTUs per shared-memory tile group
 constexpr int kGroupTasks = 21;   // 16 S + 4 M + 1 L warp tasks per group (two regions per lane)
 constexpr int kConvStages = 2;
-constexpr int kConvComputeWarps = 11;  // 12 warps per CTA = 3 per SM sub-partition -> 168 registers per thread
+#ifndef ETHCNN_CONV_COMPUTE_WARPS
+#define ETHCNN_CONV_COMPUTE_WARPS 11
+#endif
+constexpr int kConvComputeWarps = ETHCNN_CONV_COMPUTE_WARPS;  // + 1 producer warp; 12 warps -> 168 registers, 16 warps -> 128
 constexpr int kConvThreads = 32 * (1 + kConvComputeWarps);
 
 struct ConvLaunch {
