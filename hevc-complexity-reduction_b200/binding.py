@@ -54,6 +54,8 @@ def load_library() -> C.CDLL:
         "ethcnn_predict_luma_device": (i32, [vp, vp, i32, i32, sz, sz, i32, i32, vp, vp]),
         "ethcnn_export_fc1": (i32, [vp, vp, i32, i32, sz, i32, vp]),
         "ethcnn_decisions": (i32, [vp, vp, sz, vp, vp]),
+        "ethcnn_ldp_step": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp]),
+        "ethcnn_ldp_serve": (i32, [vp, cp, i32, i32]),
         "ethcnn_query": (i32, [vp, i32, C.POINTER(i64)]),
         "ethcnn_profile_enable": (i32, [vp, i32]),
         "ethcnn_profile_read": (i32, [vp, i32, C.POINTER(C.c_double), C.POINTER(i64), i32]),
@@ -176,6 +178,31 @@ class EthCnn(object):
         out = np.empty((n_frames * r * c, FC1_WIDTH), dtype=np.float32)
         _check(self._lib.ethcnn_export_fc1(self._h, _ptr(y), width, height, frame_stride, n_frames, _ptr(out)))
         return out
+
+    def ldp_step(self, luma: np.ndarray, qp: int, i_frame: int, state_in: Optional[np.ndarray] = None):
+        """One frame of the deployed LDP predictor (resi_to_cu_depth_LDP.py:114-129): luma uint8 [H, W] of the residue
+        frame, state_in float32 [nCTU, 1, 2, 448] or None (zeros).  Returns (prob [nCTU, 21], state_out [nCTU, 1, 2, 448])."""
+        luma = np.ascontiguousarray(luma, dtype=np.uint8)
+        h, w = luma.shape
+        r, c = ctu_grid(w, h)
+        n = r * c
+        prob = np.empty((n, PROBS_PER_CTU), dtype=np.float32)
+        state_out = np.empty((n, 1, 2, FC1_WIDTH), dtype=np.float32)
+        sin = None
+        if state_in is not None:
+            sin = np.ascontiguousarray(state_in, dtype=np.float32)
+            if sin.size != n * 2 * FC1_WIDTH:
+                raise EthCnnError(-1, "state_in has the wrong size")
+        _check(self._lib.ethcnn_ldp_step(self._h, _ptr(luma), w, h, qp, i_frame, _ptr(sin) if sin is not None else None,
+                                         _ptr(state_out), _ptr(prob)))
+        return prob, state_out
+
+    def ldp_serve(self, directory: str = ".", max_frames: int = 0, idle_timeout_ms: int = 0) -> int:
+        """The file-signal daemon loop (README.md:64-84); returns the number of frames served."""
+        rc = self._lib.ethcnn_ldp_serve(self._h, os.fsencode(directory), max_frames, idle_timeout_ms)
+        if rc < 0:
+            _check(rc)
+        return rc
 
     def decisions(self, prob: np.ndarray, thr6=(0.5,) * 6) -> np.ndarray:
         """HM's threshold rule on the device (TEncCu.cpp:448-462): uint8 array shaped like prob."""

@@ -95,7 +95,7 @@ __device__ __forceinline__ void heads_body(const HeadsLaunch& p, const HeadWeigh
     const int c = i % kHT, k4 = i / kHT;  // CTU fastest: conflict-free transposed store
     const int n = n0 + c;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (n < p.n_ctus) v = *reinterpret_cast<const float4*>(p.fc1 + size_t(n) * kFc1 + COL_OFF + 4 * k4);
+    if (n < p.n_ctus) v = *reinterpret_cast<const float4*>(p.fc1 + size_t(n) * p.fc1_stride + COL_OFF + 4 * k4);
     a1s[(4 * k4 + 0) * kHT + c] = v.x;
     a1s[(4 * k4 + 1) * kHT + c] = v.y;
     a1s[(4 * k4 + 2) * kHT + c] = v.z;

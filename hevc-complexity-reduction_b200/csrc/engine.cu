@@ -14,6 +14,7 @@
 #include <unistd.h>
 
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -68,6 +69,16 @@ struct DeviceModel {
   std::vector<float> h_b2, h_w2q, h_b3, h_w3q;  // host copies: b2eff / b3eff depend on the call's qp
 };
 
+// One ETH-LSTM checkpoint (HM-16.5_Test_LDP/bin/model_LDP_200000_qp*.dat, 18 tensors) on the device.
+struct LstmDeviceModel {
+  float* blob = nullptr;            // one allocation
+  const float* kernel[3] = {};      // [2n][4n]
+  const float* bias[3] = {};        // [4n]
+  HeadWeights hw[3];                // w2 = first n rows of fc2 [n+5][n2], w3 = first n2 rows of fc3 [n2+5][n3]; qp rows unused
+  std::vector<float> h_w2e, h_b2;   // host: the 5 extra-feature rows of fc2 (per head, [5][n2]) and its bias, heads side by side
+  std::vector<float> h_w3e, h_b3;   // same for fc3
+};
+
 struct ProfEvent {
   int stage;
   cudaEvent_t a, b;
@@ -102,6 +113,14 @@ struct DeviceCtx {
   int64_t prof_launches[ETHCNN_N_STAGES] = {0, 0, 0, 0};
   int last_used_tma = 0;
   int last_feat_exp = 0;
+  // LDP one-step LSTM path
+  std::map<std::string, LstmDeviceModel> lstm_models;
+  float* d_state_in = nullptr;
+  float* d_state_out = nullptr;
+  float* d_z = nullptr;
+  float* d_beff = nullptr;          // [336 + 21 (+3 pad) + 336 zeros] folded biases of the call + a zero row
+  float* h_beff = nullptr;          // pinned staging for d_beff
+  size_t lstm_rows = 0;
 };
 
 }  // namespace
@@ -113,6 +132,7 @@ struct ethcnn_handle {
   int mode = ETHCNN_MODE_AI;
   std::string model_dir;
   float t1 = 0.5f, t2 = 0.5f;
+  bool have_thr = false;
   std::vector<std::unique_ptr<DeviceCtx>> devs;
   std::mutex mu;
   std::atomic<int64_t> launches{0};
@@ -322,8 +342,18 @@ struct StageTimer {
 
 // The device-resident forward pass: everything is enqueued on `stream`, nothing is synchronised.
 // fc1_out != nullptr selects the LDP FC1 tap (conv + FC1 only, written to fc1_out [n][448]).
+struct LdpStep {             // extra inputs of the LDP CNN + one-step LSTM evaluation
+  const LstmDeviceModel* lm;
+  const float* d_state_in;   // [rows][896]
+  float* d_state_out;        // [rows][896]
+  float* d_z;                // [rows][1792]
+  const float* d_b2eff;      // [336]   b2 + efs rows folded
+  const float* d_b3eff;      // [21]
+  const float* d_zero;       // [>= 192] zeros (the qp rows are folded already)
+};
+
 int run_device(ethcnn_handle* h, DeviceCtx& c, const uint8_t* d_y, int width, int height, size_t pitch, size_t frame_stride,
-               int n_frames, int qp, float* d_out, float* fc1_out, cudaStream_t stream) {
+               int n_frames, int qp, float* d_out, float* fc1_out, cudaStream_t stream, const LdpStep* ldp = nullptr) {
   if (width <= 0 || height <= 0 || n_frames < 0 || pitch < size_t(width)) return fail(ETHCNN_E_ARG, "bad frame geometry");
   if (n_frames == 0) return ETHCNN_OK;
   CUDA_TRY(cudaSetDevice(c.device));
@@ -342,7 +372,7 @@ int run_device(ethcnn_handle* h, DeviceCtx& c, const uint8_t* d_y, int width, in
   const char* terr = nullptr;
   const bool use_tma = make_luma_tensor_map(&tmap, d_y, width, height, n_frames, pitch, frame_stride, &terr);
   c.last_used_tma = use_tma ? 1 : 0;
-  const bool gated = (h->mode == ETHCNN_MODE_AI) && fc1_out == nullptr;
+  const bool gated = ((h->mode == ETHCNN_MODE_AI) && fc1_out == nullptr) || ldp != nullptr;
   if (gated) CUDA_TRY(cudaMemsetAsync(c.flags, 0, size_t(n_frames) * chunks_per_frame * sizeof(unsigned), stream));
 
   const float in_scale = (h->mode == ETHCNN_MODE_LDP) ? (10.0f / 255.0f) : (1.0f / 255.0f);
@@ -362,6 +392,34 @@ int run_device(ethcnn_handle* h, DeviceCtx& c, const uint8_t* d_y, int width, in
       ++h->launches;
     }
     float* fc1_dst = fc1_out ? fc1_out + size_t(begin) * kFc1 : c.fc1;
+    if (ldp != nullptr) {
+      // LDP deployment: FC1 (the 448-vector) -> one LSTM step -> FC2 / FC3 on h with the five extra features folded
+      {
+        StageTimer t(c, stream, ETHCNN_STAGE_FC1);
+        CUDA_TRY(launch_fc1_tc(c.feat_hi, c.feat_lo, m->tc, m->b1, std::ldexp(1.0f, -(m->feat_exp + m->w_exp)), c.fc1, n, c.sm_count,
+                               stream));
+        ++h->launches;
+      }
+      StageTimer t(c, stream, ETHCNN_STAGE_HEADS);
+      CUDA_TRY(launch_lstm_step(c.fc1, ldp->d_state_in + size_t(begin) * 2 * kFc1, ldp->d_state_out + size_t(begin) * 2 * kFc1, ldp->d_z,
+                                ldp->lm->kernel, ldp->lm->bias, n, stream));
+      h->launches += 4;
+      HeadsLaunch hl{};
+      hl.fc1 = ldp->d_state_out + size_t(begin) * 2 * kFc1 + kFc1;   // h part of the new state rows
+      hl.fc1_stride = 2 * kFc1;
+      const int o2[3] = {0, 48, 144}, o3[3] = {0, 1, 5};
+      for (int k = 0; k < 3; ++k) {
+        hl.head[k] = ldp->lm->hw[k];
+        hl.head[k].b2 = ldp->d_b2eff + o2[k], hl.head[k].w2q = ldp->d_zero;
+        hl.head[k].b3 = ldp->d_b3eff + o3[k], hl.head[k].w3q = ldp->d_zero;
+      }
+      hl.q = 0.f;
+      hl.prob = d_out, hl.flags = c.flags, hl.t1 = h->t1, hl.t2 = h->t2;
+      hl.n_ctus = n, hl.ctu_begin = int(begin), hl.ctus_per_frame = ctus_per_frame, hl.chunks_per_frame = chunks_per_frame;
+      CUDA_TRY(launch_heads(hl, stream));
+      ++h->launches;
+      continue;
+    }
     if (h->fc1_path == 2) {  // FC1 + FC2 + FC3 in one tcgen05 kernel; a1 never leaves the SM
       FusedParams fp;
       const float q = scaled_qp(h->mode, qp);
@@ -394,6 +452,7 @@ int run_device(ethcnn_handle* h, DeviceCtx& c, const uint8_t* d_y, int width, in
     if (fc1_out) continue;
     HeadsLaunch hl{};
     hl.fc1 = c.fc1;
+    hl.fc1_stride = kFc1;
     for (int k = 0; k < 3; ++k) hl.head[k] = m->hw[k];
     hl.q = scaled_qp(h->mode, qp);
     hl.prob = d_out;
@@ -592,6 +651,158 @@ int run_host_all_devices(ethcnn_handle* h, const uint8_t* y, int width, int heig
   return ETHCNN_OK;
 }
 
+// LSTM checkpoint selection (resi_to_cu_depth_LDP.py:169-177).
+std::string lstm_prefix(int qp) {
+  if (qp < 25) return "model_LDP_200000_qp22.dat";
+  if (qp < 30) return "model_LDP_200000_qp27.dat";
+  if (qp < 35) return "model_LDP_200000_qp32.dat";
+  return "model_LDP_200000_qp37.dat";
+}
+
+int get_lstm_model(ethcnn_handle* h, DeviceCtx& c, int qp, LstmDeviceModel** out) {
+  const std::string prefix = lstm_prefix(qp);
+  auto it = c.lstm_models.find(prefix);
+  if (it != c.lstm_models.end()) {
+    *out = &it->second;
+    return ETHCNN_OK;
+  }
+  std::map<std::string, BundleTensor> t;
+  std::string err;
+  const std::string path = h->model_dir + "/" + prefix;
+  if (!read_tf_bundle(path, &t, &err)) return fail(err.find("cannot open") != std::string::npos ? ETHCNN_E_IO : ETHCNN_E_FORMAT, err);
+  static const char* hn[3] = {"64", "32", "16"};
+  const int n[3] = {64, 128, 256}, n2[3] = {48, 96, 192}, n3[3] = {1, 4, 16};
+  LstmDeviceModel m;
+  std::vector<float> blob;
+  size_t off_k[3], off_b[3], off_w2[3], off_w3[3];
+  for (int k = 0; k < 3; ++k) {
+    const std::string pre = std::string("RNN") + hn[k] + "/";
+    auto need = [&](const std::string& name, std::vector<int64_t> shape) -> const BundleTensor* {
+      auto f = t.find(pre + name);
+      if (f == t.end() || f->second.shape != shape) {
+        err = path + ": tensor " + pre + name + " missing or of unexpected shape";
+        return nullptr;
+      }
+      return &f->second;
+    };
+    const BundleTensor* kr = need("multi_rnn_cell/cell_0/lstm_cell/kernel", {2 * n[k], 4 * n[k]});
+    const BundleTensor* bs = need("multi_rnn_cell/cell_0/lstm_cell/bias", {4 * n[k]});
+    const BundleTensor* w2 = need("fc2/full_connect_w", {n[k] + 5, n2[k]});
+    const BundleTensor* b2 = need("fc2/full_connect_b", {n2[k]});
+    const BundleTensor* w3 = need("fc3/full_connect_w", {n2[k] + 5, n3[k]});
+    const BundleTensor* b3 = need("fc3/full_connect_b", {n3[k]});
+    if (!kr || !bs || !w2 || !b2 || !w3 || !b3) return fail(ETHCNN_E_FORMAT, err);
+    auto push = [&](const float* p, size_t cnt) {
+      while (blob.size() % 4) blob.push_back(0.f);
+      const size_t o = blob.size();
+      blob.insert(blob.end(), p, p + cnt);
+      return o;
+    };
+    off_k[k] = push(kr->data.data(), kr->data.size());
+    off_b[k] = push(bs->data.data(), bs->data.size());
+    off_w2[k] = push(w2->data.data(), size_t(n[k]) * n2[k]);     // rows of h; the 5 extra-feature rows stay on the host
+    off_w3[k] = push(w3->data.data(), size_t(n2[k]) * n3[k]);
+    m.h_w2e.insert(m.h_w2e.end(), w2->data.begin() + size_t(n[k]) * n2[k], w2->data.end());
+    m.h_b2.insert(m.h_b2.end(), b2->data.begin(), b2->data.end());
+    m.h_w3e.insert(m.h_w3e.end(), w3->data.begin() + size_t(n2[k]) * n3[k], w3->data.end());
+    m.h_b3.insert(m.h_b3.end(), b3->data.begin(), b3->data.end());
+  }
+  int rc = upload(&m.blob, blob.data(), blob.size() * 4);
+  if (rc) return rc;
+  for (int k = 0; k < 3; ++k) {
+    m.kernel[k] = m.blob + off_k[k], m.bias[k] = m.blob + off_b[k];
+    m.hw[k].w2 = m.blob + off_w2[k], m.hw[k].w3 = m.blob + off_w3[k];
+  }
+  auto ins = c.lstm_models.emplace(prefix, std::move(m));
+  *out = &ins.first->second;
+  return ETHCNN_OK;
+}
+
+// One frame of the deployed LDP predictor: residual ETH-CNN + one LSTM step + heads + gates
+// (resi_to_cu_depth_LDP.py:114-129, net_CNN_LSTM_one_step.py:266-323).  Host pointers; state_in may be NULL (zeros).
+int run_ldp_step(ethcnn_handle* h, const uint8_t* y, int width, int height, int qp, int i_frame, const float* state_in,
+                 float* state_out, float* prob) {
+  if (h->mode != ETHCNN_MODE_LDP) return fail(ETHCNN_E_ARG, "the LSTM step requires ETHCNN_MODE_LDP");
+  if (!h->have_thr) return fail(ETHCNN_E_IO, "Thr_info.txt was not found: the LSTM step needs its gate thresholds");
+  if (width <= 0 || height <= 0) return fail(ETHCNN_E_ARG, "bad frame geometry");
+  DeviceCtx& c = *h->devs[0];
+  CUDA_TRY(cudaSetDevice(c.device));
+  LstmDeviceModel* lm = nullptr;
+  int rc = get_lstm_model(h, c, qp, &lm);
+  if (rc) return rc;
+  const size_t rows = size_t((width + kCtu - 1) / kCtu) * ((height + kCtu - 1) / kCtu);
+  const size_t pitch = (size_t(width) + 15) / 16 * 16, dev_frame = pitch * height;
+  if ((rc = ensure_staging(c, dev_frame, rows * kProbs, false, false))) return rc;
+  if (rows > c.lstm_rows) {
+    cudaFree(c.d_state_in), cudaFree(c.d_state_out), cudaFree(c.d_z);
+    c.d_state_in = c.d_state_out = c.d_z = nullptr;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c.d_state_in), rows * 2 * kFc1 * 4));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c.d_state_out), rows * 2 * kFc1 * 4));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c.d_z), std::min(rows, h->chunk_ctus) * 4 * kFc1 * 4));
+    c.lstm_rows = rows;
+  }
+  constexpr int kBeff = 336 + 24 + 336;
+  if (!c.d_beff) {
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c.d_beff), kBeff * 4));
+    CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&c.h_beff), kBeff * 4));
+  }
+  // the five extra inputs of FC2 / FC3 are identical for every CTU of the frame: fold their rows into the biases
+  const float efs[5] = {scaled_qp(ETHCNN_MODE_LDP, qp), (i_frame % 4 + 4) % 4 == 0 ? 1.f : 0.f, (i_frame % 4 + 4) % 4 == 1 ? 1.f : 0.f,
+                        (i_frame % 4 + 4) % 4 == 2 ? 1.f : 0.f, (i_frame % 4 + 4) % 4 == 3 ? 1.f : 0.f};
+  const int n2[3] = {48, 96, 192}, n3[3] = {1, 4, 16};
+  memset(c.h_beff, 0, kBeff * 4);
+  {
+    size_t o2 = 0, o3 = 0, e2 = 0, e3 = 0;
+    for (int k = 0; k < 3; ++k) {
+      for (int j = 0; j < n2[k]; ++j) {
+        float v = lm->h_b2[o2 + j];
+        for (int e = 0; e < 5; ++e) v = std::fmaf(efs[e], lm->h_w2e[e2 + size_t(e) * n2[k] + j], v);
+        c.h_beff[o2 + j] = v;
+      }
+      for (int j = 0; j < n3[k]; ++j) {
+        float v = lm->h_b3[o3 + j];
+        for (int e = 0; e < 5; ++e) v = std::fmaf(efs[e], lm->h_w3e[e3 + size_t(e) * n3[k] + j], v);
+        c.h_beff[336 + o3 + j] = v;
+      }
+      o2 += n2[k], o3 += n3[k], e2 += 5 * size_t(n2[k]), e3 += 5 * size_t(n3[k]);
+    }
+  }
+  cudaStream_t s = c.s_compute;
+  CUDA_TRY(cudaMemcpyAsync(c.d_beff, c.h_beff, kBeff * 4, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpy2DAsync(c.d_slab[0], pitch, y, width, width, height, cudaMemcpyHostToDevice, s));
+  if (state_in) {
+    CUDA_TRY(cudaMemcpyAsync(c.d_state_in, state_in, rows * 2 * kFc1 * 4, cudaMemcpyHostToDevice, s));
+  } else {
+    CUDA_TRY(cudaMemsetAsync(c.d_state_in, 0, rows * 2 * kFc1 * 4, s));
+  }
+  LdpStep ls{lm, c.d_state_in, c.d_state_out, c.d_z, c.d_beff, c.d_beff + 336, c.d_beff + 360};
+  if ((rc = run_device(h, c, c.d_slab[0], width, height, pitch, dev_frame, 1, qp, c.d_prob[0], nullptr, s, &ls))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(prob, c.d_prob[0], rows * kProbs * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(state_out, c.d_state_out, rows * 2 * kFc1 * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return ETHCNN_OK;
+}
+
+bool file_exists(const std::string& p) {
+  struct stat st;
+  return stat(p.c_str(), &st) == 0;
+}
+
+bool read_exact(const std::string& path, void* dst, size_t bytes) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  const size_t got = fread(dst, 1, bytes, f);
+  fclose(f);
+  return got == bytes;
+}
+
+bool write_all(const std::string& path, const void* src, size_t bytes) {
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) return false;
+  const size_t put = bytes ? fwrite(src, 1, bytes, f) : 0;
+  return (fclose(f) == 0) && put == bytes;
+}
+
 int open_device(ethcnn_handle* h, int device) {
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
@@ -622,6 +833,8 @@ void close_device(DeviceCtx& c) {
   cudaSetDevice(c.device);
   cudaDeviceSynchronize();
   for (auto& kv : c.models) free_model(kv.second);
+  for (auto& kv : c.lstm_models) cudaFree(kv.second.blob);
+  cudaFree(c.d_state_in), cudaFree(c.d_state_out), cudaFree(c.d_z), cudaFree(c.d_beff), cudaFreeHost(c.h_beff);
   cudaFree(c.feat_hi), cudaFree(c.feat_lo), cudaFree(c.fc1), cudaFree(c.flags);
   for (int i = 0; i < DeviceCtx::kSlabs; ++i) {
     cudaFree(c.d_slab[i]), cudaFree(c.d_prob[i]), cudaFreeHost(c.h_stage[i]), cudaFreeHost(c.h_prob[i]);
@@ -645,10 +858,12 @@ int create_common(const char* model_dir, const char* thr_path, int mode, const s
   h->mode = mode;
   h->model_dir = (model_dir && *model_dir) ? model_dir : ".";
   if (const char* e = getenv("ETHCNN_FC1")) h->fc1_path = (strcmp(e, "simt") == 0) ? 0 : (strcmp(e, "tc") == 0 ? 1 : 2);
-  if (mode == ETHCNN_MODE_AI) {
+  {
     const std::string tp = thr_path ? std::string(thr_path) : h->model_dir + "/Thr_info.txt";
     int rc = read_thresholds(tp, &h->t1, &h->t2);
-    if (rc) return rc;
+    h->have_thr = (rc == ETHCNN_OK);
+    // the AI script cannot run without Thr_info.txt (net_CNN.py:47); the LDP CNN-only entry points can
+    if (rc && (mode == ETHCNN_MODE_AI || thr_path)) return rc;
   }
   for (int d : devices) {
     int rc = open_device(h.get(), d);
@@ -769,6 +984,71 @@ int ethcnn_predict_yuv_file(ethcnn_handle* h, const char* yuv_path, int width, i
     return fail(ETHCNN_E_IO, std::string("cannot rename onto ") + out_path);
   }
   return ETHCNN_OK;
+}
+
+int ethcnn_ldp_step(ethcnn_handle* h, const uint8_t* y, int width, int height, int qp, int i_frame, const float* state_in,
+                    float* state_out, float* prob) {
+  if (!h || !y || !state_out || !prob) return fail(ETHCNN_E_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lock(h->mu);
+  return run_ldp_step(h, y, width, height, qp, i_frame, state_in, state_out, prob);
+}
+
+int ethcnn_ldp_serve(ethcnn_handle* h, const char* dir, int max_frames, int idle_timeout_ms) {
+  if (!h) return fail(ETHCNN_E_ARG, "NULL handle");
+  const std::string d = (dir && *dir) ? std::string(dir) + "/" : std::string();
+  const std::string start_file = d + "pred_start.sig", end_file = d + "pred_end.sig", command_file = d + "command.dat";
+  const std::string yuv_file = d + "resi.yuv", state_file = d + "state.dat", save_file = d + "cu_depth.dat";
+  int served = 0;
+  auto last = std::chrono::steady_clock::now();
+  std::vector<uint8_t> luma;
+  std::vector<float> state_in, state_out, prob;
+  while (max_frames <= 0 || served < max_frames) {
+    if (!file_exists(start_file)) {
+      if (idle_timeout_ms > 0 &&
+          std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - last).count() > idle_timeout_ms)
+        break;
+      std::this_thread::sleep_for(std::chrono::microseconds(200));
+      continue;
+    }
+    // command.dat: "<i_frame> <width> <height> <qp> [end]" (resi_to_cu_depth_LDP.py:54-70); anything else = not ready yet
+    int i_frame = -1, w = -1, hgt = -1, qp = -1;
+    {
+      FILE* f = fopen(command_file.c_str(), "r");
+      char tail[16] = {0};
+      if (f) {
+        char line[256] = {0};
+        if (fgets(line, sizeof(line), f) && sscanf(line, "%d %d %d %d %15s", &i_frame, &w, &hgt, &qp, tail) == 5 &&
+            strcmp(tail, "[end]") == 0) {
+        } else {
+          i_frame = -1;
+        }
+        fclose(f);
+      }
+    }
+    if (i_frame < 0) {
+      std::this_thread::sleep_for(std::chrono::microseconds(200));
+      continue;
+    }
+    remove(start_file.c_str());
+    if (w <= 0 || hgt <= 0) return fail(ETHCNN_E_ARG, "command.dat carries a bad frame size");
+    const size_t rows = size_t((w + kCtu - 1) / kCtu) * ((hgt + kCtu - 1) / kCtu);
+    luma.resize(size_t(w) * hgt);
+    if (!read_exact(yuv_file, luma.data(), luma.size())) return fail(ETHCNN_E_IO, "cannot read " + yuv_file);
+    state_in.assign(rows * 2 * kFc1, 0.f);
+    state_out.resize(rows * 2 * kFc1);
+    prob.resize(rows * kProbs);
+    if (i_frame > 1 && !read_exact(state_file, state_in.data(), state_in.size() * 4))   // :103-112: zeros when i_frame <= 1
+      return fail(ETHCNN_E_IO, "cannot read " + state_file);
+    int rc = ethcnn_ldp_step(h, luma.data(), w, hgt, qp, i_frame, state_in.data(), state_out.data(), prob.data());
+    if (rc) return rc;
+    // same order as save_cu_depth_and_state (:131-144): state, probabilities, then the end signal
+    if (!write_all(state_file, state_out.data(), state_out.size() * 4) || !write_all(save_file, prob.data(), prob.size() * 4) ||
+        !write_all(end_file, nullptr, 0))
+      return fail(ETHCNN_E_IO, "cannot write the result files");
+    ++served;
+    last = std::chrono::steady_clock::now();
+  }
+  return served;
 }
 
 int ethcnn_decisions(ethcnn_handle* h, const float* prob, size_t n_ctus, const float thr6[6], uint8_t* decision) {

@@ -75,7 +75,8 @@ struct HeadWeights {         // one head (64 / 32 / 16); all device pointers
 };
 
 struct HeadsLaunch {
-  const float* fc1;          // [n_ctus][448] after bias + leaky
+  const float* fc1;          // [n_ctus][fc1_stride] input activations (FC1 output, or the LSTM h for the LDP step)
+  int fc1_stride;            // floats between rows (448, or 896 when reading h out of the LSTM state rows)
   HeadWeights head[3];
   float q;                   // scaled qp
   float* prob;               // [total][21], row of CTU i at prob + (ctu_begin + i) * 21
@@ -100,6 +101,10 @@ cudaError_t launch_heads(const HeadsLaunch& p, cudaStream_t stream);
 
 cudaError_t launch_gate(float* prob, const unsigned* flags, float t2, long long n_total, int ctus_per_frame,
                         int chunks_per_frame, cudaStream_t stream);
+
+// One LSTM step for the three heads (lstm_stage.cu).  state rows are [c(448) | h(448)]; z_scratch is [rows][1792].
+cudaError_t launch_lstm_step(const float* fc1, const float* state_in, float* state_out, float* z_scratch,
+                             const float* const kernel[3], const float* const bias[3], int rows, cudaStream_t stream);
 
 cudaError_t launch_decisions(const float* prob, unsigned char* dec, long long n_values, const float* thr6_dev,
                              cudaStream_t stream);

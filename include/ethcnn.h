@@ -100,6 +100,28 @@ int ethcnn_predict_luma_device(ethcnn_handle* h, const uint8_t* d_y, int width, 
 int ethcnn_export_fc1(ethcnn_handle* h, const uint8_t* y, int width, int height, size_t frame_stride,
                       int n_frames, float* out);
 
+/*
+ * The deployed inter-mode (LDP) predictor for ONE frame: residual ETH-CNN -> one step of the three ETH-LSTM cells
+ * -> FC2 / FC3 with the five extra features [qp/51*0.18, one_hot(i_frame % 4)] -> gates.  Replaces
+ * predict_cu_depth() of HM-16.5_Test_LDP/bin/resi_to_cu_depth_LDP.py:114-129 (graph: net_CNN_LSTM_one_step.py:266-323).
+ *   y          luma of the residue frame (resi.yuv: resi + 128 clipped), width * height bytes, host
+ *   state_in   nCTU * 2 * 448 floats ([c | h] per CTU, heads 64|128|256 side by side) or NULL for zeros
+ *   state_out  same shape; prob nCTU * 21 floats.  LSTM checkpoints model_LDP_200000_qp{22,27,32,37}.dat are chosen
+ *              by QP range (resi_to_cu_depth_LDP.py:169-177) from model_dir; Thr_info.txt supplies the gate thresholds.
+ * Requires ETHCNN_MODE_LDP.
+ */
+int ethcnn_ldp_step(ethcnn_handle* h, const uint8_t* y, int width, int height, int qp, int i_frame,
+                    const float* state_in, float* state_out, float* prob);
+
+/*
+ * The file-signal daemon of the LDP encoder (README.md:64-84; HM side TEncGOP.cpp(LDP):1471-1505; Python side
+ * resi_to_cu_depth_LDP.py:146-187): polls <dir>/pred_start.sig, reads command.dat ("<frame> <W> <H> <QP> [end]"),
+ * resi.yuv and (for frame > 1) state.dat, runs ethcnn_ldp_step, writes state.dat, cu_depth.dat, then pred_end.sig.
+ * Weights stay on the device between frames.  Returns the number of frames served (>= 0) once max_frames (> 0) have
+ * been served or nothing arrived for idle_timeout_ms (> 0); with both <= 0 it serves forever like the reference.
+ */
+int ethcnn_ldp_serve(ethcnn_handle* h, const char* dir, int max_frames, int idle_timeout_ms);
+
 /* HM's use of a probability (TLibEncoder/TEncCu.cpp:448-462): 2 = split only (p > up), 0 = no split
  * (p <= down), 1 = check both.  thr6 = the six numbers of Thr_info.txt (up,down per depth,
  * TEncCu.cpp:250).  Runs on the device; prob/decision are HOST arrays of n_ctus*21 entries. */

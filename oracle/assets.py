@@ -25,7 +25,10 @@ GOLDEN = os.path.join(REPO, "tests", "golden")
 AI_MODELS = {22: "model_2000000_qp20~25.dat", 27: "model_2000000_qp25~30.dat",
              32: "model_2000000_qp30~35.dat", 37: "model_2000000_qp35~40.dat"}
 LDP_MODEL = "model_LDP_2000000_qp22~37.dat"
-NPZ = {"model_2000000_qp30~35.dat": "weights_ai_qp30_35.npz", LDP_MODEL: "weights_ldp_cnn.npz"}
+LDP_LSTM_MODELS = {22: "model_LDP_200000_qp22.dat", 27: "model_LDP_200000_qp27.dat",
+                   32: "model_LDP_200000_qp32.dat", 37: "model_LDP_200000_qp37.dat"}
+NPZ = {"model_2000000_qp30~35.dat": "weights_ai_qp30_35.npz", LDP_MODEL: "weights_ldp_cnn.npz",
+       LDP_LSTM_MODELS[32]: "weights_ldp_lstm_qp32.npz"}
 SUFFIXES = (".index", ".data-00000-of-00001")
 
 
@@ -38,7 +41,7 @@ def stage_from_reference() -> int:
     """Copy the 5 CNN checkpoints + Thr_info.txt from /root/reference into oracle/_ref/checkpoints.
     Returns the number of files copied (0 when the reference is absent)."""
     n = 0
-    for kind, names in (("AI", list(AI_MODELS.values())), ("LDP", [LDP_MODEL])):
+    for kind, names in (("AI", list(AI_MODELS.values())), ("LDP", [LDP_MODEL] + list(LDP_LSTM_MODELS.values()))):
         src_dir = _source_dirs(kind)[0]
         if not os.path.isdir(src_dir):
             continue
@@ -56,11 +59,14 @@ def stage_from_reference() -> int:
     return n
 
 
-def materialize(dst_dir: str, kind: str = "AI", thr_line: str = "0.5 0.5 0.5 0.5 0.5 0.5") -> List[str]:
+LDP_THR_LINE = "0.4 0.6 0.3 0.7 0.2 0.8"   # HM-16.5_Test_LDP/bin/Thr_info.txt (down, up per depth)
+
+
+def materialize(dst_dir: str, kind: str = "AI", thr_line: str = None) -> List[str]:
     """Populate dst_dir with every available checkpoint of `kind` (+ Thr_info.txt) the way the encoder's
     working directory holds them.  Returns the model prefixes now present."""
     os.makedirs(dst_dir, exist_ok=True)
-    names = list(AI_MODELS.values()) if kind == "AI" else [LDP_MODEL]
+    names = list(AI_MODELS.values()) if kind == "AI" else [LDP_MODEL] + list(LDP_LSTM_MODELS.values())
     present = []
     for name in names:
         done = False
@@ -79,13 +85,13 @@ def materialize(dst_dir: str, kind: str = "AI", thr_line: str = "0.5 0.5 0.5 0.5
         if done:
             present.append(name)
     with open(os.path.join(dst_dir, "Thr_info.txt"), "w") as f:
-        f.write(thr_line)
+        f.write(thr_line if thr_line is not None else ("0.5 0.5 0.5 0.5 0.5 0.5" if kind == "AI" else LDP_THR_LINE))
     return present
 
 
 def load_weights(name: str) -> Dict[str, np.ndarray]:
     """Checkpoint `name` (a model prefix) as {tensor: float32 array} from whichever source exists."""
-    kind = "LDP" if name == LDP_MODEL else "AI"
+    kind = "LDP" if name.startswith("model_LDP") else "AI"
     for src_dir in _source_dirs(kind):
         if all(os.path.exists(os.path.join(src_dir, name + suf)) for suf in SUFFIXES):
             return tf_bundle.read_bundle(os.path.join(src_dir, name))

@@ -207,6 +207,108 @@ def fc1_export(ctus: np.ndarray, qp: float, weights: Dict[str, np.ndarray], dtyp
     return fc1
 
 
+# ----------------------------------------------------------------------------- LDP: one-step ETH-LSTM heads
+LSTM_HEADS = (("64", 64, 48, 1), ("32", 128, 96, 4), ("16", 256, 192, 16))
+LDP_LSTM_MODELS = {22: "model_LDP_200000_qp22.dat", 27: "model_LDP_200000_qp27.dat",
+                   32: "model_LDP_200000_qp32.dat", 37: "model_LDP_200000_qp37.dat"}
+
+
+def ldp_lstm_model_prefix(qp: int) -> str:
+    """LSTM checkpoint selection, HM-16.5_Test_LDP/bin/resi_to_cu_depth_LDP.py:169-177."""
+    if qp < 25:
+        return LDP_LSTM_MODELS[22]
+    elif qp < 30:
+        return LDP_LSTM_MODELS[27]
+    elif qp < 35:
+        return LDP_LSTM_MODELS[32]
+    return LDP_LSTM_MODELS[37]
+
+
+def random_lstm_weights(seed: int) -> Dict[str, np.ndarray]:
+    """Synthetic LSTM checkpoint in the reference's 18-tensor layout (names as written by TF for
+    net_CNN_LSTM_one_step.py:201-264)."""
+    rng = np.random.default_rng(seed)
+    w: Dict[str, np.ndarray] = {}
+    for h, n, n2, n3 in LSTM_HEADS:
+        pre = "RNN%s/" % h
+        w[pre + "multi_rnn_cell/cell_0/lstm_cell/kernel"] = (rng.standard_normal((2 * n, 4 * n)) * (1.0 / math.sqrt(2 * n))).astype(np.float32)
+        w[pre + "multi_rnn_cell/cell_0/lstm_cell/bias"] = (rng.standard_normal(4 * n) * 0.1).astype(np.float32)
+        w[pre + "fc2/full_connect_w"] = (rng.standard_normal((n + 5, n2)) * (1.3 / math.sqrt(n))).astype(np.float32)
+        w[pre + "fc2/full_connect_b"] = (rng.standard_normal(n2) * 0.05).astype(np.float32)
+        w[pre + "fc3/full_connect_w"] = (rng.standard_normal((n2 + 5, n3)) * (1.3 / math.sqrt(n2))).astype(np.float32)
+        w[pre + "fc3/full_connect_b"] = (rng.standard_normal(n3) * 0.05).astype(np.float32)
+    return w
+
+
+def lstm_cell_step(x, c_prev, h_prev, kernel, bias, forget_bias=1.0, cell_clip=5.0):
+    """tf.contrib.rnn.LSTMCell (TensorFlow 1.x rnn_cell_impl.LSTMCell.call, no peepholes, no projection), as
+    instantiated at net_CNN_LSTM_one_step.py:205-206: gate columns in the order (i, j, f, o);
+    c = sigmoid(f + forget_bias) * c_prev + sigmoid(i) * tanh(j), clipped to +-cell_clip; h = sigmoid(o) * tanh(c)."""
+    dt = x.dtype
+    z = np.concatenate([x, h_prev], axis=1) @ kernel.astype(dt) + bias.astype(dt)
+    i, j, f, o = np.split(z, 4, axis=1)
+    c = _sigmoid(f + dt.type(forget_bias)) * c_prev + _sigmoid(i) * np.tanh(j)
+    c = np.clip(c, dt.type(-cell_clip), dt.type(cell_clip))
+    h = _sigmoid(o) * np.tanh(c)
+    return c.astype(dt), h.astype(dt)
+
+
+def ldp_lstm_forward(ctus: np.ndarray, qp: int, i_frame: int, state_in: np.ndarray, cnn_w, lstm_w,
+                     thresholds: Tuple[float, float], dtype=np.float32):
+    """One `sess.run` of the deployed LDP predictor on ONE sub-batch (net_CNN_LSTM_one_step.py:266-323):
+    residual ETH-CNN up to FC1 (:151-199) -> three one-step LSTMs (:201-264) -> FC2 / FC3 with the five extra
+    features [qp/51*0.18, one_hot(i_frame % 4)] -> gates on THR_L1_LOWER / THR_L2_LOWER (:304,310).
+    state_in: [B, 1, 2, 448] (c then h, heads 64|128|256 side by side).  Returns ([B,21], state_out)."""
+    ctus = np.asarray(ctus)
+    n = ctus.shape[0]
+    x, _ = input_scaling(ctus, qp, MODE_LDP, dtype)
+    _, vec = fc_heads(conv_features(x, cnn_w), np.zeros((n, 1), dtype), cnn_w, return_fc1=True)   # resi_cnn(): the 448-vector
+    q = dtype(qp) / dtype(51.0) * dtype(0.18)                                                    # :281
+    efs = np.zeros((n, 5), dtype)
+    efs[:, 0] = q
+    efs[:, 1 + int(i_frame) % 4] = 1                                                             # tf.one_hot(i_frame_in_GOP, depth=4)
+    state_in = np.asarray(state_in, dtype).reshape(n, 2, 448)
+    state_out = np.zeros((n, 2, 448), dtype)
+    ys = []
+    off = 0
+    for h, nh, _n2, _n3 in LSTM_HEADS:
+        pre = "RNN%s/" % h
+        c, hh = lstm_cell_step(vec[:, off:off + nh].astype(dtype), state_in[:, 0, off:off + nh], state_in[:, 1, off:off + nh],
+                               lstm_w[pre + "multi_rnn_cell/cell_0/lstm_cell/kernel"], lstm_w[pre + "multi_rnn_cell/cell_0/lstm_cell/bias"])
+        state_out[:, 0, off:off + nh], state_out[:, 1, off:off + nh] = c, hh
+        a2 = _leaky(np.concatenate([hh, efs], 1) @ lstm_w[pre + "fc2/full_connect_w"].astype(dtype) + lstm_w[pre + "fc2/full_connect_b"].astype(dtype))
+        y = _sigmoid(np.concatenate([a2, efs], 1) @ lstm_w[pre + "fc3/full_connect_w"].astype(dtype) + lstm_w[pre + "fc3/full_connect_b"].astype(dtype))
+        ys.append(y.astype(dtype))
+        off += nh
+    y64, y32, y16 = ys
+    t1, t2 = np.float32(thresholds[0]), np.float32(thresholds[1])
+    if np.count_nonzero(y64.astype(np.float32) > t1) == 0:      # :304
+        y32 = np.zeros_like(y32)
+    if np.count_nonzero(y32.astype(np.float32) > t2) == 0:      # :310 (sees the gated y32)
+        y16 = np.zeros_like(y16)
+    return np.concatenate([y64, y32, y16], axis=1), state_out.reshape(n, 1, 2, 448)
+
+
+def ldp_predict_frame(luma: np.ndarray, qp: int, i_frame: int, state_in: Optional[np.ndarray], cnn_w, lstm_w,
+                      thresholds: Tuple[float, float], dtype=np.float32):
+    """resi_to_cu_depth_LDP.py:72-129 for one residue frame: zero-pad, slice CTUs in raster order, mini-batches of
+    1024 through the net; state_in None = zeros (the script uses zeros when i_frame <= 1, :103-112)."""
+    h, w = luma.shape
+    vh, vw = math.ceil(h / 64) * 64, math.ceil(w / 64) * 64
+    pad = np.zeros((vh, vw), np.uint8)
+    pad[:h, :w] = luma
+    ctus = frame_to_ctus(pad)
+    n = ctus.shape[0]
+    if state_in is None:
+        state_in = np.zeros((n, 1, 2, 448), dtype)
+    prob = np.zeros((n, N_OUT), dtype)
+    state_out = np.zeros((n, 1, 2, 448), dtype)
+    for s in range(0, n, SUB_BATCH):
+        e = min(s + SUB_BATCH, n)
+        prob[s:e], state_out[s:e] = ldp_lstm_forward(ctus[s:e], qp, i_frame, state_in[s:e], cnn_w, lstm_w, thresholds, dtype)
+    return prob.astype(np.float32), state_out.astype(np.float32)
+
+
 # ----------------------------------------------------------------------------- driver restatement
 def get_Y_for_one_frame(buf: memoryview, frame_index: int, frame_width: int, frame_height: int,
                         image_size: int = IMAGE_SIZE) -> np.ndarray:

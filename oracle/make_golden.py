@@ -133,6 +133,50 @@ def run_reference_resi_cnn(ctus: np.ndarray) -> np.ndarray:
             sys.modules.pop(m, None)
 
 
+def run_reference_ldp_daemon_functions(frames, width, height, qps):
+    """HM-16.5_Test_LDP/bin/resi_to_cu_depth_LDP.py (unmodified): import the module (builds the CNN + one-step LSTM
+    graph through net_CNN_LSTM_one_step.net), restore the CNN and the per-QP LSTM checkpoints the way its main loop
+    does (:158-178), then call its own get_images_from_one_file / get_state_in_from_one_file / predict_cu_depth /
+    save_cu_depth_and_state for a sequence of residue frames.  Returns per frame (cu_depth [n,21], state [n,1,2,448])."""
+    old_path, old_cwd = list(sys.path), os.getcwd()
+    work = tempfile.mkdtemp(prefix="ethcnn_golden_")
+    try:
+        shutil.copy(os.path.join(LDP_BIN, "Thr_info.txt"), os.path.join(work, "Thr_info.txt"))
+        for fn in os.listdir(LDP_BIN):
+            if fn.startswith("model_") and not fn.endswith(".meta"):
+                os.symlink(os.path.join(LDP_BIN, fn), os.path.join(work, fn))
+        os.chdir(work)
+        tf = _fresh_tf()
+        for m in ("resi_to_cu_depth_LDP", "net_CNN_LSTM_one_step", "config"):
+            sys.modules.pop(m, None)
+        sys.path.insert(0, LDP_BIN)
+        mod = importlib.import_module("resi_to_cu_depth_LDP")
+        mod.state_file = "state.dat"   # a global its __main__ block defines (:150) and get_state_in_from_one_file reads
+        mod.saver_CNN.restore(mod.sess, "model_LDP_2000000_qp22~37.dat")
+        out = []
+        qp_last = None
+        for i_frame, (luma, qp) in enumerate(zip(frames, qps), start=1):
+            if qp != qp_last:   # :165-178
+                name = ("model_LDP_200000_qp22.dat" if qp < 25 else "model_LDP_200000_qp27.dat" if qp < 30 else
+                        "model_LDP_200000_qp32.dat" if qp < 35 else "model_LDP_200000_qp37.dat")
+                mod.saver_LSTM.restore(mod.sess, name)
+                qp_last = qp
+            with open("resi.yuv", "wb") as f:
+                f.write(luma.tobytes() + bytes([128]) * (width * height // 2))
+            images, num_vectors = mod.get_images_from_one_file("resi.yuv", width, height, 64)
+            state_in = mod.get_state_in_from_one_file("state.dat", num_vectors, i_frame)
+            depth_out, state_out = mod.predict_cu_depth(images, state_in, qp, i_frame)
+            mod.save_cu_depth_and_state(depth_out, state_out, "cu_depth.dat", "state.dat", "pred_end.sig", num_vectors)
+            out.append((np.fromfile("cu_depth.dat", "<f4").reshape(-1, 21), np.fromfile("state.dat", "<f4").reshape(-1, 1, 2, 448)))
+        return out
+    finally:
+        os.chdir(old_cwd)
+        shutil.rmtree(work, ignore_errors=True)
+        sys.path[:] = old_path
+        for m in ("resi_to_cu_depth_LDP", "net_CNN_LSTM_one_step", "config"):
+            sys.modules.pop(m, None)
+
+
 def demo_ctus() -> np.ndarray:
     d = np.fromfile(os.path.join(REF, "ETH-CNN_Training_AI", "Data", "AI_Test_5000.dat_shuffled"), dtype=np.uint8)
     return d.reshape(5000, 4992)[:, :4096].reshape(5000, 64, 64)
@@ -155,19 +199,28 @@ QPS = (22, 27, 32, 37)
 
 
 def main():
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="", help="comma-separated fixture stems to (re)generate; default all")
+    only = set(x for x in ap.parse_args().only.split(",") if x)
+
+    def want(stem):
+        return not only or stem in only
     os.makedirs(OUT, exist_ok=True)
     real = demo_ctus()
 
     # A. padding in both directions, two frames, procedural content
     w, h = 200, 136
     yuv = eo.synth_yuv(w, h, 2, seed0=100)
-    np.savez_compressed(os.path.join(OUT, "ai_pad_200x136_f2.npz"), yuv=np.frombuffer(yuv, np.uint8), width=w, height=h,
+    if want("ai_pad_200x136_f2"):
+      np.savez_compressed(os.path.join(OUT, "ai_pad_200x136_f2.npz"), yuv=np.frombuffer(yuv, np.uint8), width=w, height=h,
                         qps=np.array(QPS), **{"prob_qp%d" % q: run_reference_script(yuv, w, h, q) for q in QPS})
 
     # B. mosaic of real CTUs (realistic spread of probabilities)
     luma = mosaic(real[:40], 5, 8)
     yuv = yuv_from_luma([luma])
-    np.savez_compressed(os.path.join(OUT, "ai_mosaic_512x320.npz"), yuv=np.frombuffer(yuv, np.uint8), width=512, height=320,
+    if want("ai_mosaic_512x320"):
+      np.savez_compressed(os.path.join(OUT, "ai_mosaic_512x320.npz"), yuv=np.frombuffer(yuv, np.uint8), width=512, height=320,
                         qps=np.array(QPS), **{"prob_qp%d" % q: run_reference_script(yuv, 512, 320, q) for q in QPS})
 
     # C. gates: 64x64 "video" -- every frame is its own sub-batch of one CTU.
@@ -181,7 +234,8 @@ def main():
     flat = np.full((1, 64, 64), 128, np.uint8)
     frames = list(real[sel]) + [flat[0]]
     yuv = yuv_from_luma(frames)
-    np.savez_compressed(os.path.join(OUT, "ai_gates_64x64_f10.npz"), yuv=np.frombuffer(yuv, np.uint8), width=64, height=64,
+    if want("ai_gates_64x64_f10"):
+      np.savez_compressed(os.path.join(OUT, "ai_gates_64x64_f10.npz"), yuv=np.frombuffer(yuv, np.uint8), width=64, height=64,
                         qps=np.array([32]), prob_qp32=run_reference_script(yuv, 64, 64, 32))
 
     # C2. a frame with more than 1024 CTUs: 33 x 32 = 1056 -> sub-batches 1024 + 32; textured band at the
@@ -190,42 +244,70 @@ def main():
     luma = np.full((h, w), 128, np.uint8)
     luma[:128, :1024] = mosaic(real[100:132], 2, 16)
     yuv = yuv_from_luma([luma])
-    np.savez_compressed(os.path.join(OUT, "ai_subbatch_2112x2048.npz"), yuv=np.frombuffer(yuv, np.uint8), width=w, height=h,
+    if want("ai_subbatch_2112x2048"):
+      np.savez_compressed(os.path.join(OUT, "ai_subbatch_2112x2048.npz"), yuv=np.frombuffer(yuv, np.uint8), width=w, height=h,
                         qps=np.array([32]), prob_qp32=run_reference_script(yuv, w, h, 32))
 
     # C3. non-default thresholds (tokens [1] and [3] are the ones the script reads)
     luma = mosaic(real[200:212], 3, 4)
     yuv = yuv_from_luma([luma, np.full_like(luma, 77)])
     thr_line = "0.9 0.95 0.8 0.7 0.6 0.4"
-    np.savez_compressed(os.path.join(OUT, "ai_thr_256x192_f2.npz"), yuv=np.frombuffer(yuv, np.uint8), width=256, height=192,
+    if want("ai_thr_256x192_f2"):
+      np.savez_compressed(os.path.join(OUT, "ai_thr_256x192_f2.npz"), yuv=np.frombuffer(yuv, np.uint8), width=256, height=192,
                         qps=np.array([27]), thr_line=np.array(thr_line), prob_qp27=run_reference_script(yuv, 256, 192, 27, thr_line))
 
     # D. BASELINE config 1: 768x512, 1 frame, QP 32 -- input regenerated from the recipe at test time
     w, h = 768, 512
     yuv = eo.synth_yuv(w, h, 1, seed0=1)
-    np.savez_compressed(os.path.join(OUT, "ai_cfg1_768x512.npz"), width=w, height=h, seed0=1, n_frames=1,
+    if want("ai_cfg1_768x512"):
+      np.savez_compressed(os.path.join(OUT, "ai_cfg1_768x512.npz"), width=w, height=h, seed0=1, n_frames=1,
                         yuv_sha256=np.array(hashlib.sha256(yuv).hexdigest()), qps=np.array([32]),
                         prob_qp32=run_reference_script(yuv, w, h, 32))
 
     # E. LDP residual CNN (config 5 arithmetic): residue-like CTUs + a few real ones
     resi = eo.frame_to_ctus(eo.synth_residue_frame(512, 256, 7))
     ctus = np.concatenate([resi, eo.known_answer_ctus(), real[:6]])
-    np.savez_compressed(os.path.join(OUT, "ldp_ctus.npz"), ctus=ctus, qps=np.array([22, 37]),
+    if want("ldp_ctus"):
+      np.savez_compressed(os.path.join(OUT, "ldp_ctus.npz"), ctus=ctus, qps=np.array([22, 37]),
                         prob_qp22=run_reference_ldp_net(ctus, 22), prob_qp37=run_reference_ldp_net(ctus, 37),
                         fc1_vector=run_reference_resi_cnn(ctus))
 
+    # E2. the deployed LDP predictor (CNN + one-step ETH-LSTM) over a 5-frame residue sequence with a QP switch,
+    # state carried through state.dat exactly as the daemon does
+    w, h = 200, 136
+    frames = [eo.synth_residue_frame(w, h, 20 + k) for k in range(5)]
+    frames[3] = np.full((h, w), 128, np.uint8)          # an all-flat residue frame (gates close)
+    qps = [32, 32, 32, 32, 22]
+    if want("ldp_lstm_200x136_f5"):
+        res = run_reference_ldp_daemon_functions(frames, w, h, qps)
+        np.savez_compressed(os.path.join(OUT, "ldp_lstm_200x136_f5.npz"), frames=np.stack(frames), width=w, height=h, qps=np.array(qps),
+                            cu_depth=np.stack([r[0] for r in res]), state=np.stack([r[1] for r in res]))
+    # E3. a first frame that is completely flat (zero LSTM state): y64 stays under THR_L1_LOWER, both gates close;
+    # and a 2112x2048 residue frame (1056 CTUs: mini-batches of 1024 + 32, the second one flat)
+    if want("ldp_lstm_gates"):
+        flat = [np.full((64, 128), 128, np.uint8)]
+        res_flat = run_reference_ldp_daemon_functions(flat, 128, 64, [37])
+        big = np.full((2048, 2112), 128, np.uint8)
+        big[:128, :1024] = eo.synth_residue_frame(1024, 128, 31)
+        res_big = run_reference_ldp_daemon_functions([big], 2112, 2048, [27])
+        np.savez_compressed(os.path.join(OUT, "ldp_lstm_gates.npz"), flat=flat[0], flat_cu_depth=res_flat[0][0], flat_state=res_flat[0][1],
+                            big=big, big_cu_depth=res_big[0][0], big_state=res_big[0][1])
+
     # F. raw-CTU AI vectors (ungated single sub-batch semantics are covered by C; these pin the net itself)
     ctus = np.concatenate([eo.known_answer_ctus(), real[300:330]])
-    out = {}
-    for q in QPS:
-        yuv = yuv_from_luma(list(ctus))  # 64x64 frames
-        out["prob_qp%d" % q] = run_reference_script(yuv, 64, 64, q, "0.5 -1 0.5 -1 0.5 -1")  # gates always open
-    np.savez_compressed(os.path.join(OUT, "ai_ctus_ungated.npz"), ctus=ctus, qps=np.array(QPS), **out)
+    if want("ai_ctus_ungated"):
+        out = {}
+        for q in QPS:
+            yuv = yuv_from_luma(list(ctus))  # 64x64 frames
+            out["prob_qp%d" % q] = run_reference_script(yuv, 64, 64, q, "0.5 -1 0.5 -1 0.5 -1")  # gates always open
+        np.savez_compressed(os.path.join(OUT, "ai_ctus_ungated.npz"), ctus=ctus, qps=np.array(QPS), **out)
     # G. the two checkpoints the GPU box needs for real-weight parity, as {tensor name: float32 array}
     # (re-serialised into TF bundles at test time by oracle/assets.materialize)
     from oracle import assets, tf_bundle
     for name, npz in assets.NPZ.items():
-        src = os.path.join(LDP_BIN if name == assets.LDP_MODEL else AI_BIN, name)
+        if not want(npz[:-4]):
+            continue
+        src = os.path.join(AI_BIN if name.startswith("model_2000000") else LDP_BIN, name)
         np.savez_compressed(os.path.join(OUT, npz), **tf_bundle.read_bundle(src, verify_crc=True))
     print("golden fixtures written to", OUT)
     for fn in sorted(os.listdir(OUT)):

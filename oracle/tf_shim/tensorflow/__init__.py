@@ -23,7 +23,11 @@ from __future__ import annotations
 import os as _os
 import sys as _sys
 
+import builtins as _builtins
+
 import numpy as _np
+
+_builtin_slice = _builtins.slice
 
 float32 = _np.float32
 _F = _np.float32
@@ -41,6 +45,8 @@ _NAME_COUNTS = {}
 def _reset_default_graph():
     del _TRAINABLE[:]
     _NAME_COUNTS.clear()
+    _SCOPED_VARS.clear()
+    del _SCOPE[:]
 
 
 reset_default_graph = _reset_default_graph
@@ -49,7 +55,7 @@ reset_default_graph = _reset_default_graph
 def _as_tensor(v):
     if isinstance(v, Tensor):
         return v
-    return Tensor(lambda env, _v=v: _np.asarray(_v, dtype=_F) if not isinstance(_v, (bool, _np.bool_)) else _v, (),
+    return Tensor(lambda env, _v=v: _np.asarray(_v, dtype=_F) if not isinstance(_v, (_builtins.bool, _np.bool_)) else _v, (),
                   "Const")
 
 
@@ -123,6 +129,50 @@ def trainable_variables():
     return list(_TRAINABLE)
 
 
+# ----------------------------------------------------------------------------- variable scopes / get_variable
+_SCOPE = []
+_SCOPED_VARS = {}
+
+
+class _VarScope(object):
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        _SCOPE.append(self.name)
+        return self
+
+    def __exit__(self, *a):
+        _SCOPE.pop()
+        return False
+
+    def reuse_variables(self):
+        pass
+
+
+def variable_scope(name_or_scope, reuse=None, **kw):
+    return _VarScope(name_or_scope if isinstance(name_or_scope, str) else name_or_scope.name)
+
+
+def get_variable_scope():
+    return _VarScope("/".join(_SCOPE))
+
+
+def get_variable(name, shape=None, dtype=None, initializer=None, trainable=True):
+    full = "/".join(_SCOPE + [name])
+    if full in _SCOPED_VARS:
+        return _SCOPED_VARS[full]
+    v = Variable.__new__(Variable)
+    v._value = None
+    v._init = constant(0.0, shape=shape)
+    Tensor.__init__(v, lambda env, _v=v: _v._read(), (), "VariableV2", name=full + ":0", static_shape=shape)
+    v.var_name = full
+    _SCOPED_VARS[full] = v
+    if trainable:
+        _TRAINABLE.append(v)
+    return v
+
+
 def placeholder(dtype, shape=None, name=None):
     t = Tensor(None, (), "Placeholder", name=name, static_shape=shape)
 
@@ -174,7 +224,38 @@ def matmul(a, b, name=None):
 
 
 def multiply(a, b, name=None):
+    if isinstance(b, (list, tuple)):   # tf.multiply(1.0, [t0, t1, ...]) packs the list into one tensor first
+        b = stack(list(b), axis=0)
     return _as_tensor(a) * b
+
+
+def slice(input_, begin, size, name=None):  # noqa: A001
+    def fn(env, v):
+        idx = tuple(_builtin_slice(b, None if sz == -1 else b + sz) for b, sz in zip(begin, size))
+        return v[idx]
+    return Tensor(fn, (_as_tensor(input_),), "Slice")
+
+
+def split(value, num_or_size_splits, axis=0, name=None):
+    n = int(num_or_size_splits)
+    return [Tensor(lambda env, v, _i=i: _np.split(v, n, axis=axis)[_i], (_as_tensor(value),), "Split") for i in range(n)]
+
+
+def one_hot(indices, depth, axis=-1, dtype=None, name=None):
+    def fn(env, v):
+        idx = _np.asarray(v).astype(_np.int64)
+        out = (idx[..., None] == _np.arange(depth)).astype(_F)
+        if axis not in (-1, idx.ndim):
+            out = _np.moveaxis(out, -1, axis)
+        return out
+    return Tensor(fn, (_as_tensor(indices),), "OneHot")
+
+
+def to_int32(x, name=None):
+    return Tensor(lambda env, v: _np.asarray(v).astype(_np.int32), (_as_tensor(x),), "Cast")
+
+
+bool = "bool"  # noqa: A001  (tf.bool, only ever passed to tf.cast)
 
 
 def cond(pred, true_fn=None, false_fn=None, name=None, fn1=None, fn2=None):
@@ -183,7 +264,7 @@ def cond(pred, true_fn=None, false_fn=None, name=None, fn1=None, fn2=None):
     p = _as_tensor(pred)
 
     def fn(env):
-        return t_branch._eval(env) if bool(p._eval(env)) else f_branch._eval(env)
+        return t_branch._eval(env) if _builtins.bool(p._eval(env)) else f_branch._eval(env)
     return Tensor(fn, (), "Cond")
 
 
@@ -203,6 +284,8 @@ to_float = _lazy_unary(lambda v: _np.asarray(v, dtype=_F), "Cast")
 
 
 def cast(x, dtype=None, name=None):
+    if dtype == "bool":
+        return Tensor(lambda env, v: _np.asarray(v).astype(_np.bool_), (_as_tensor(x),), "Cast")
     return Tensor(lambda env, v: _np.asarray(v, dtype=_F), (_as_tensor(x),), "Cast")
 
 
@@ -320,6 +403,94 @@ image = _Image()
 
 
 # ----------------------------------------------------------------------------- tf.train / Session
+# ----------------------------------------------------------------------------- tf.contrib.rnn (one-step use only)
+class _LSTMStateTuple(tuple):
+    def __new__(cls, c, h):
+        return tuple.__new__(cls, (c, h))
+
+    c = property(lambda self: self[0])
+    h = property(lambda self: self[1])
+
+
+class _LSTMCell(object):
+    """tf.contrib.rnn.LSTMCell (TF 1.x rnn_cell_impl.LSTMCell.call) without peepholes / projection:
+    gates (i, j, f, o) = split([x, h_prev] kernel + bias); c = sigmoid(f + forget_bias) c_prev + sigmoid(i) tanh(j),
+    clipped to +-cell_clip; h = sigmoid(o) tanh(c).  Variables: <scope>/lstm_cell/{kernel,bias}."""
+
+    def __init__(self, num_units, forget_bias=1.0, cell_clip=None, state_is_tuple=True, **kw):
+        self.n, self.forget_bias, self.cell_clip = int(num_units), _F(forget_bias), cell_clip
+
+    def __call__(self, inputs, state):
+        c_prev, h_prev = state
+        n = self.n
+        with variable_scope("lstm_cell"):
+            in_dim = None
+            kernel_holder = {}
+
+            def fn(env, x, c0, h0):
+                k = kernel_holder["k"]._eval(env)
+                b = kernel_holder["b"]._eval(env)
+                z = (_np.concatenate([x, h0], axis=1).astype(_F) @ k + b).astype(_F)
+                i, j, f, o = _np.split(z, 4, axis=1)
+                sig = lambda v: (_F(1) / (_F(1) + _np.exp(-v, dtype=_F))).astype(_F)
+                c = (sig(f + self.forget_bias) * c0 + sig(i) * _np.tanh(j)).astype(_F)
+                if self.cell_clip is not None:
+                    c = _np.clip(c, _F(-self.cell_clip), _F(self.cell_clip))
+                h = (sig(o) * _np.tanh(c)).astype(_F)
+                return (c, h)
+            # input width is only known from the checkpoint: kernel is [in + n, 4n]
+            kernel_holder["k"] = get_variable("kernel", None)
+            kernel_holder["b"] = get_variable("bias", [4 * n])
+            both = Tensor(fn, (_as_tensor(inputs), _as_tensor(c_prev), _as_tensor(h_prev)), "LSTMCell")
+        c_new = Tensor(lambda env, v: v[0], (both,), "LSTMCell_c")
+        h_new = Tensor(lambda env, v: v[1], (both,), "LSTMCell_h")
+        return h_new, _LSTMStateTuple(c_new, h_new)
+
+
+class _DropoutWrapper(object):
+    def __init__(self, cell, input_keep_prob=1.0, output_keep_prob=1.0, **kw):
+        self.cell, self.keep = cell, _as_tensor(output_keep_prob)
+
+    def __call__(self, inputs, state):
+        out, new_state = self.cell(inputs, state)
+        keep = self.keep
+
+        def fn(env, v, kp):
+            if float(kp) != 1.0:
+                raise RuntimeError("shim: dropout must be inactive at inference (isdrop=0)")
+            return v   # x / 1 * floor(1 + uniform[0,1)) == x
+        return Tensor(fn, (out, keep), "Dropout"), new_state
+
+
+class _MultiRNNCell(object):
+    def __init__(self, cells, state_is_tuple=True):
+        self.cells = list(cells)
+
+    def __call__(self, inputs, state):
+        cur = inputs
+        new_states = []
+        with variable_scope("multi_rnn_cell"):
+            for i, cell in enumerate(self.cells):
+                with variable_scope("cell_%d" % i):
+                    cur, st = cell(cur, state[i])
+                    new_states.append(st)
+        return cur, tuple(new_states)
+
+
+class _Rnn(object):
+    LSTMCell = _LSTMCell
+    DropoutWrapper = _DropoutWrapper
+    MultiRNNCell = _MultiRNNCell
+    LSTMStateTuple = _LSTMStateTuple
+
+
+class _Contrib(object):
+    rnn = _Rnn()
+
+
+contrib = _Contrib()
+
+
 class _SaverDef(object):
     V1 = 1
     V2 = 2

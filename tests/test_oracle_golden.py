@@ -135,3 +135,39 @@ def test_driver_restatement_edge_cases():
     assert eo.get_prob(b"", 64, 64, 32, w).shape == (0, 21)          # empty file: zero frames
     luma = eo.get_Y_for_one_frame(memoryview(eo.synth_yuv(72, 40, 1)), 0, 72, 40)
     assert luma.shape == (64, 128) and (luma[40:] == 0).all() and (luma[:, 72:] == 0).all()
+
+
+def test_ldp_lstm_oracle_matches_reference_daemon_functions(golden_dir):
+    """The one-step ETH-LSTM restatement against the vectors produced by the reference's unmodified
+    resi_to_cu_depth_LDP.py functions (5-frame residue sequence, state carried through state.dat, QP switch)."""
+    g = np.load(os.path.join(golden_dir, "ldp_lstm_200x136_f5.npz"))
+    cnn = assets.load_weights(assets.LDP_MODEL)
+    thr = (0.6, 0.7)   # tokens [1], [3] of HM-16.5_Test_LDP/bin/Thr_info.txt
+    state = None
+    checked = 0
+    for k, (luma, qp) in enumerate(zip(g["frames"], g["qps"]), start=1):
+        try:
+            lw = assets.load_weights(eo.ldp_lstm_model_prefix(int(qp)))
+        except FileNotFoundError:
+            break
+        prob, state = eo.ldp_predict_frame(luma, int(qp), k, state if k > 1 else None, cnn, lw, thr)
+        assert np.abs(prob - g["cu_depth"][k - 1]).max() <= 2e-5
+        assert np.abs(state - g["state"][k - 1]).max() <= 5e-5
+        assert np.array_equal(eo.decisions(prob, (0.6, 0.4, 0.7, 0.3, 0.8, 0.2)), eo.decisions(g["cu_depth"][k - 1], (0.6, 0.4, 0.7, 0.3, 0.8, 0.2)))
+        state = g["state"][k - 1]   # continue from the reference's own state so errors do not compound
+        checked += 1
+    assert checked >= 4
+
+
+def test_ldp_lstm_gates(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ldp_lstm_gates.npz"))
+    assert (g["flat_cu_depth"][:, 1:] == 0).all() and (g["flat_cu_depth"][:, 0] < 0.6).all()
+    cnn = assets.load_weights(assets.LDP_MODEL)
+    for key, qp in (("flat", 37), ("big", 27)):
+        try:
+            lw = assets.load_weights(eo.ldp_lstm_model_prefix(qp))
+        except FileNotFoundError:
+            continue
+        prob, state = eo.ldp_predict_frame(g[key], qp, 1, None, cnn, lw, (0.6, 0.7))
+        assert np.abs(prob - g[key + "_cu_depth"]).max() <= 2e-5 and np.array_equal(prob == 0, g[key + "_cu_depth"] == 0)
+        assert np.abs(state - g[key + "_state"]).max() <= 5e-5
