@@ -75,3 +75,45 @@ def test_hm_bitstream_identical_for_cuda_and_oracle_probabilities(tmp_path, name
     np.ones_like(p_oracle).astype("<f4").tofile(const_dat)
     md5_k, _ = run_hm(str(tmp_path / "k"), yuv_path, w, h, nf, qp, const_dat)
     assert md5_k != md5_o
+
+
+LDP_HM = "/root/reference/HM-16.5_Test_LDP/bin/TAppEncoderStatic"
+
+
+@pytest.mark.skipif(not os.path.exists(LDP_HM), reason="prebuilt LDP encoder not on this box")
+def test_hm_ldp_bitstream_identical_with_cuda_made_answers(tmp_path):
+    """Inter mode: the unmodified prebuilt LDP encoder (two passes per frame, file-signal handshake, README.md:64-84)
+    answered (a) by the oracle and (b) by the probabilities the CUDA predictor computed on the B200 for the very residue
+    frames HM produced (tests/golden/cuda_ldp_hm_prob.npy via tools/make_cuda_fixture.py).  The residue frames of run
+    (b) must equal the recorded ones frame by frame and the bitstream must be identical."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import ldp_hm_capture as cap
+
+    g = np.load(os.path.join(GOLDEN, "ldp_hm_capture.npz"))
+    fixture = os.path.join(GOLDEN, "cuda_ldp_hm_prob.npy")
+    md5_o, size_o, seen_o = cap.run_hm_ldp(str(tmp_path / "o"), cap.oracle_answerer())
+    os.makedirs(tmp_path / "o", exist_ok=True)
+    assert (md5_o, size_o) == (str(g["str_md5"]), int(g["str_size"]))            # the capture is reproducible
+    assert all(np.array_equal(s[1], r) for s, r in zip(seen_o, g["resi"]))
+    if not os.path.exists(fixture):
+        pytest.skip("no CUDA-made LDP fixture committed yet")
+    cuda_prob = np.load(fixture)
+    assert np.abs(cuda_prob - g["oracle_prob"]).max() <= 1e-4
+    thr6 = (0.6, 0.4, 0.7, 0.3, 0.8, 0.2)
+    assert np.array_equal(eo.decisions(cuda_prob, thr6), eo.decisions(g["oracle_prob"], thr6))
+    served = {"k": 0}
+
+    def replay(i_frame, fw, fh, q, luma):
+        k = served["k"]
+        if not (int(g["i_frames"][k]) == i_frame and np.array_equal(luma, g["resi"][k])):
+            served.setdefault("diverged_at", i_frame)      # checked after the run (an assert here would hang HM)
+        served["k"] += 1
+        return cuda_prob[k], np.zeros((cuda_prob[k].shape[0], 1, 2, 448), np.float32)   # HM never reads state.dat
+    md5_c, size_c, _ = cap.run_hm_ldp(str(tmp_path / "c"), replay)
+    assert "diverged_at" not in served, "HM's residue differs from the recorded run at frame %d" % served["diverged_at"]
+    assert (md5_c, size_c) == (md5_o, size_o)
+    # sensitivity: all-ones probabilities change the bitstream
+    md5_k, _, _ = cap.run_hm_ldp(str(tmp_path / "k"), lambda i, fw, fh, q, luma: (np.ones((cuda_prob[0].shape[0], 21), np.float32),
+                                                                                   np.zeros((cuda_prob[0].shape[0], 1, 2, 448), np.float32)))
+    assert md5_k != md5_o

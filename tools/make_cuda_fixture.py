@@ -30,6 +30,21 @@ def main():
         subprocess.run([cli, yuv, str(w), str(h), str(qp)], cwd=work, check=True)
         os.replace(os.path.join(work, "cu_depth.dat"), os.path.join(out_dir, "cuda_%s.cu_depth.dat" % name))
         print("wrote", name)
+    # LDP: the CUDA predictor over the residue frames the prebuilt LDP encoder produced (tools/ldp_hm_capture.py)
+    import numpy as np
+
+    import ethcnn_b200 as eb
+    cap = np.load(os.path.join(ROOT, "tests", "golden", "ldp_hm_capture.npz"))
+    lwork = tempfile.mkdtemp()
+    present = assets.materialize(lwork, "LDP")
+    if eo.ldp_lstm_model_prefix(int(cap["qp"])) in present:
+        probs, state = [], None
+        with eb.EthCnn(lwork, None, eb.MODE_LDP, device=0) as net:
+            for i_frame, luma in zip(cap["i_frames"], cap["resi"]):
+                prob, state = net.ldp_step(luma, int(cap["qp"]), int(i_frame), state if i_frame > 1 else None)
+                probs.append(prob)
+        np.save(os.path.join(out_dir, "cuda_ldp_hm_prob.npy"), np.stack(probs))
+        print("wrote cuda_ldp_hm_prob.npy")
 
 
 if __name__ == "__main__":
