@@ -857,6 +857,10 @@ int create_common(const char* model_dir, const char* thr_path, int mode, const s
   std::unique_ptr<ethcnn_handle> h(new ethcnn_handle());
   h->mode = mode;
   h->model_dir = (model_dir && *model_dir) ? model_dir : ".";
+  if (const char* e = getenv("ETHCNN_CHUNK_CTUS")) {
+    const long v = atol(e);
+    if (v >= 1 && v <= (1 << 22)) h->chunk_ctus = size_t(v);
+  }
   if (const char* e = getenv("ETHCNN_FC1")) h->fc1_path = (strcmp(e, "simt") == 0) ? 0 : (strcmp(e, "tc") == 0 ? 1 : 2);
   {
     const std::string tp = thr_path ? std::string(thr_path) : h->model_dir + "/Thr_info.txt";

@@ -10,9 +10,10 @@
 // Tiles.  M = 128 CTUs (one TMEM lane per CTU).  N is split on head boundaries so FC2 stays inside a CTA:
 //   type 1: head 16        FC1 N = 256 (cols 192..447), FC2 K = 256 (4 slices), N = 192, FC3 192 -> 16
 //   type 0: heads 64 + 32  FC1 N = 192 (cols 0..191),   FC2 64 -> 48 (1 slice) and 128 -> 96 (2 slices)
-// All type-1 tiles come first in the static tile order, so a persistent CTA gets a balanced mix.
+// The static tile order pairs the two tiles of an M block on neighbouring CTAs (tile_of).
 //
-// One shared-memory ring (2 stages x 96 KB, 128-byte swizzle, K slices of 64) carries BOTH contractions:
+// One shared-memory ring (2 stages x 96 KB of 128-byte-swizzled K = 64 slices; -DETHCNN_FC_BK=32 builds 4 stages
+// x 48 KB with 64-byte swizzle instead) carries BOTH contractions:
 //   FC1 stage: A_hi, A_lo (features, TMA) + B_hi, B_lo (W1 slice, TMA)
 //   FC2 stage: A_hi, A_lo = the tile's own FC1 activations, written by the epilogue warps straight from
 //              TMEM (bias + leaky + re-split) into the swizzled layout + B_hi, B_lo (W2 slice, TMA)
@@ -29,24 +30,30 @@
 namespace ethcnn {
 namespace {
 
-constexpr int kBM = 128, kBK = 64;
-constexpr int kStages = 2;
-constexpr int kABytes = kBM * kBK * 2;                       // 16384
-constexpr int kStageBytes = 2 * kABytes + 2 * 256 * kBK * 2; // 98304
-constexpr int kKSteps = kFeat / kBK;                         // 42
+#ifndef ETHCNN_FC_BK
+#define ETHCNN_FC_BK 64
+#endif
+constexpr int kBM = 128, kBK = ETHCNN_FC_BK;                 // K slice = one swizzle row: 64 fp16 (128 B) or 32 fp16 (64 B)
+static_assert(kBK == 64 || kBK == 32, "K slice must be one 128-byte or one 64-byte swizzle row");
+constexpr int kRowBytes = kBK * 2;
+constexpr int kStages = 192 * 1024 / (2 * kBM * kRowBytes + 2 * 256 * kRowBytes);   // 2 (K = 64) or 4 (K = 32)
+constexpr int kABytes = kBM * kRowBytes;                     // 16384 | 8192
+constexpr int kStageBytes = 2 * kABytes + 2 * 256 * kRowBytes; // 98304 | 49152
+constexpr int kKSteps = kFeat / kBK;                         // 42 | 84
 constexpr int kAcc2Col = 256;                                // TMEM column of accumulator 2
 constexpr int kThreads = 192;
 constexpr int kW3Floats = 48 * 1 + 96 * 4 + 192 * 16;        // 3504
 constexpr int kTableFloats = kW3Floats + 336 + 21 + kFc1 + 3; // w3 | b2eff | b3eff | b1 (padded to 16 B)
 constexpr int kSmemBytes = kStages * kStageBytes + kTableFloats * 4 + 256 + 1024;
 
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+// K-major operand tile in swizzled shared memory: rows of kBK fp16 (one swizzle row), 8-row groups back to back.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= uint64_t((smem_addr & 0x3ffffu) >> 4);  // start address  [0,14)
   d |= uint64_t(1) << 16;                      // leading byte offset (ignored for swizzled K-major)
-  d |= uint64_t(1024 >> 4) << 32;              // stride byte offset: 8 rows x 128 B
+  d |= uint64_t((8 * kRowBytes) >> 4) << 32;   // stride byte offset: one 8-row group
   d |= uint64_t(1) << 46;                      // descriptor version (sm_100)
-  d |= uint64_t(2) << 61;                      // SWIZZLE_128B
+  d |= uint64_t(kBK == 64 ? 2 : 4) << 61;      // SWIZZLE_128B | SWIZZLE_64B
   return d;
 }
 // kind::f16 instruction descriptor: D fp32, A = B = fp16, K-major both, M = 128, N as given.
@@ -98,10 +105,17 @@ struct TileInfo {
   int n1;        // FC1 N
   int nslices;   // FC2 K slices (= n1 / 64)
 };
-__device__ __forceinline__ TileInfo decode_tile(int t, int m_tiles) {
+// Static tile order: CTAs 2j and 2j+1 work on the SAME 128 CTUs at the same time, one on the head-16 columns and
+// one on the head-64/32 columns, and swap roles every iteration (type-1 tiles cost 4/3 of type-0 tiles).  The
+// feature slices of an M tile are therefore requested twice within a few microseconds and come from HBM once.
+__device__ __forceinline__ int tile_of(int cta, int iter, int n_ctas, int m_tiles) {
+  const int m = (cta >> 1) + (n_ctas >> 1) * iter;
+  return m < m_tiles ? 2 * m + ((cta ^ iter) & 1) : -1;
+}
+__device__ __forceinline__ TileInfo decode_tile(int t, int /*m_tiles*/) {
   TileInfo ti;
-  ti.type = t < m_tiles ? 1 : 0;
-  ti.m0 = (ti.type ? t : t - m_tiles) * kBM;
+  ti.type = t & 1;
+  ti.m0 = (t >> 1) * kBM;
   ti.n0 = ti.type ? 192 : 0;
   ti.n1 = ti.type ? 256 : 192;
   ti.nslices = ti.n1 / kBK;
@@ -111,10 +125,10 @@ __device__ __forceinline__ TileInfo decode_tile(int t, int m_tiles) {
 __device__ __forceinline__ void fc2_slice(int type, int j, int& head, int& kofs, int& n2, int& acc_col, int& first) {
   if (type) {
     head = 2, kofs = j * kBK, n2 = 192, acc_col = 0, first = (j == 0);
-  } else if (j == 0) {
-    head = 0, kofs = 0, n2 = 48, acc_col = 0, first = 1;
+  } else if (j < 64 / kBK) {
+    head = 0, kofs = j * kBK, n2 = 48, acc_col = 0, first = (j == 0);
   } else {
-    head = 1, kofs = (j - 1) * kBK, n2 = 96, acc_col = 48, first = (j == 1);
+    head = 1, kofs = (j - 64 / kBK) * kBK, n2 = 96, acc_col = 48, first = (j == 64 / kBK);
   }
 }
 
@@ -134,17 +148,17 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   float* b3s = b2s + 336;              // [21] (+3 pad)
   float* b1s = b3s + 24;               // [448]
   uint64_t* bars = reinterpret_cast<uint64_t*>(tab + kTableFloats);
-  uint64_t* full = bars;               // [kStages]  TMA bytes landed
-  uint64_t* empty = bars + 2;          // [kStages]  MMAs that read the stage have retired
-  uint64_t* a2_full = bars + 4;        // [kStages]  epilogue warps have written the FC2 A operand
-  uint64_t* acc1_full = bars + 6;      // FC1 accumulator complete
-  uint64_t* acc1_empty = bars + 7;     // epilogue has drained accumulator 1
-  uint64_t* acc2_full = bars + 8;
-  uint64_t* acc2_empty = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* full = bars;                        // [kStages]  TMA bytes landed
+  uint64_t* empty = bars + kStages;             // [kStages]  MMAs that read the stage have retired
+  uint64_t* a2_full = bars + 2 * kStages;       // [kStages]  epilogue warps have written the FC2 A operand
+  uint64_t* acc1_full = bars + 3 * kStages;     // FC1 accumulator complete
+  uint64_t* acc1_empty = acc1_full + 1;         // epilogue has drained accumulator 1
+  uint64_t* acc2_full = acc1_full + 2;
+  uint64_t* acc2_empty = acc1_full + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc1_full + 4);
+  static_assert((3 * kStages + 5) * 8 <= 256, "barrier block overflows its shared-memory slot");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles = 2 * m_tiles;
 
   for (int i = threadIdx.x; i < kW3Floats; i += kThreads) w3s[i] = p.w3[i];
   for (int i = threadIdx.x; i < 336; i += kThreads) b2s[i] = p.b2eff[i];
@@ -154,7 +168,7 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a_hi), prefetch_tmap(&map_a_lo);
     prefetch_tmap(&w1_hi_t0), prefetch_tmap(&w1_lo_t0), prefetch_tmap(&w1_hi_t1), prefetch_tmap(&w1_lo_t1);
-    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1), mbar_init(&empty[s], 1), mbar_init(&a2_full[s], 4);
+    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 2), mbar_init(&empty[s], 1), mbar_init(&a2_full[s], 4);
     mbar_init(acc1_full, 1), mbar_init(acc1_empty, 4), mbar_init(acc2_full, 1), mbar_init(acc2_empty, 4);
     mbar_fence_init();
   }
@@ -169,21 +183,41 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer ------------------------------------------------
-    if (lane == 0) {
+    // Issuing a TMA costs the issuing thread a few hundred cycles, so the work is spread over three lanes that walk
+    // the ring in lockstep (all wait on the same empty barrier): lane 0 loads the A tiles (features), lane 1 the B
+    // tiles (weights), lane 2 runs an L2 prefetch of the feature slices a few stages ahead (they come from HBM: a
+    // chunk of features is larger than L2).  full[s] therefore expects two arrivals, each with its own byte count.
+#ifndef ETHCNN_FC_L2_PREFETCH
+#define ETHCNN_FC_L2_PREFETCH (384 / ETHCNN_FC_BK)
+#endif
+    if (lane < 3) {
       int it = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int iter = 0, t; (t = tile_of(blockIdx.x, iter, gridDim.x, m_tiles)) >= 0; ++iter) {
         const TileInfo ti = decode_tile(t, m_tiles);
         const CUtensorMap* wh = ti.type ? &w1_hi_t1 : &w1_hi_t0;
         const CUtensorMap* wl = ti.type ? &w1_lo_t1 : &w1_lo_t0;
+        if (lane == 2) {
+          for (int ks = 0; ks < ETHCNN_FC_L2_PREFETCH && ks < kKSteps; ++ks) {
+            tma_prefetch_l2_2d(&map_a_hi, ks * kBK, ti.m0);
+            tma_prefetch_l2_2d(&map_a_lo, ks * kBK, ti.m0);
+          }
+        }
         for (int ks = 0; ks < kKSteps; ++ks, ++it) {
           const int s = it % kStages;
           mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
           uint8_t* st = smem + s * kStageBytes;
-          mbar_arrive_expect_tx(&full[s], 2 * kABytes + 2 * ti.n1 * kBK * 2);
-          tma_load_2d(st, &map_a_hi, &full[s], ks * kBK, ti.m0);
-          tma_load_2d(st + kABytes, &map_a_lo, &full[s], ks * kBK, ti.m0);
-          tma_load_2d(st + 2 * kABytes, wh, &full[s], ks * kBK, ti.n0);
-          tma_load_2d(st + 2 * kABytes + ti.n1 * kBK * 2, wl, &full[s], ks * kBK, ti.n0);
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&full[s], 2 * kABytes);
+            tma_load_2d(st, &map_a_hi, &full[s], ks * kBK, ti.m0);
+            tma_load_2d(st + kABytes, &map_a_lo, &full[s], ks * kBK, ti.m0);
+          } else if (lane == 1) {
+            mbar_arrive_expect_tx(&full[s], 2 * ti.n1 * kBK * 2);
+            tma_load_2d(st + 2 * kABytes, wh, &full[s], ks * kBK, ti.n0);
+            tma_load_2d(st + 2 * kABytes + ti.n1 * kBK * 2, wl, &full[s], ks * kBK, ti.n0);
+          } else if (ks + ETHCNN_FC_L2_PREFETCH < kKSteps) {
+            tma_prefetch_l2_2d(&map_a_hi, (ks + ETHCNN_FC_L2_PREFETCH) * kBK, ti.m0);
+            tma_prefetch_l2_2d(&map_a_lo, (ks + ETHCNN_FC_L2_PREFETCH) * kBK, ti.m0);
+          }
         }
         for (int j = 0; j < ti.nslices; ++j, ++it) {  // FC2 stages: only the W2 slice comes through TMA
           const int s = it % kStages;
@@ -191,18 +225,22 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           uint8_t* st = smem + s * kStageBytes;
           int head, kofs, n2, acc_col, first;
           fc2_slice(ti.type, j, head, kofs, n2, acc_col, first);
-          const CUtensorMap* bh = head == 0 ? &w2_hi_0 : (head == 1 ? &w2_hi_1 : &w2_hi_2);
-          const CUtensorMap* bl = head == 0 ? &w2_lo_0 : (head == 1 ? &w2_lo_1 : &w2_lo_2);
-          mbar_arrive_expect_tx(&full[s], 2 * n2 * kBK * 2);
-          tma_load_2d(st + 2 * kABytes, bh, &full[s], kofs, 0);
-          tma_load_2d(st + 2 * kABytes + n2 * kBK * 2, bl, &full[s], kofs, 0);
+          if (lane == 0) {
+            mbar_arrive(&full[s]);
+          } else if (lane == 1) {
+            const CUtensorMap* bh = head == 0 ? &w2_hi_0 : (head == 1 ? &w2_hi_1 : &w2_hi_2);
+            const CUtensorMap* bl = head == 0 ? &w2_lo_0 : (head == 1 ? &w2_lo_1 : &w2_lo_2);
+            mbar_arrive_expect_tx(&full[s], 2 * n2 * kBK * 2);
+            tma_load_2d(st + 2 * kABytes, bh, &full[s], kofs, 0);
+            tma_load_2d(st + 2 * kABytes + n2 * kBK * 2, bl, &full[s], kofs, 0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer ------------------------------------------------
-    int it = 0, tile_i = 0, a2_cnt[kStages] = {0, 0};
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_i) {
+    int it = 0, tile_i = 0, a2_cnt[kStages] = {};
+    for (int t; (t = tile_of(blockIdx.x, tile_i, gridDim.x, m_tiles)) >= 0; ++tile_i) {
       const TileInfo ti = decode_tile(t, m_tiles);
       mbar_wait(acc1_empty, (tile_i & 1) ^ 1);
       tc_fence_after();
@@ -213,8 +251,13 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         tc_fence_after();
         if (lane == 0) {
           const uint32_t base = smem_u32(smem + s * kStageBytes);
-          const uint64_t da_hi = umma_desc_sw128(base), da_lo = umma_desc_sw128(base + kABytes);
-          const uint64_t db_hi = umma_desc_sw128(base + 2 * kABytes), db_lo = umma_desc_sw128(base + 2 * kABytes + ti.n1 * kBK * 2);
+          const uint64_t da_hi = umma_desc(base), da_lo = umma_desc(base + kABytes);
+          const uint64_t db_hi = umma_desc(base + 2 * kABytes), db_lo = umma_desc(base + 2 * kABytes + ti.n1 * kBK * 2);
+#ifdef ETHCNN_EXPERIMENT_NO_MMA   // measurement only: one MMA per stage instead of twelve
+          for (int k = 0; k < 1; ++k) {
+            umma_f16(tmem_base, da_hi, db_hi, idesc1, (ks | k) != 0);
+          }
+#else
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             const uint64_t adv = uint64_t(k * 32 >> 4);  // 16 fp16 = 32 bytes along K inside the swizzle atom
@@ -222,6 +265,7 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             umma_f16(tmem_base, da_hi + adv, db_lo + adv, idesc1, 1);
             umma_f16(tmem_base, da_lo + adv, db_hi + adv, idesc1, 1);
           }
+#endif
           umma_commit(&empty[s]);
           if (ks == kKSteps - 1) umma_commit(acc1_full);
         }
@@ -240,8 +284,8 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         tc_fence_after();
         if (lane == 0) {
           const uint32_t base = smem_u32(smem + s * kStageBytes);
-          const uint64_t da_hi = umma_desc_sw128(base), da_lo = umma_desc_sw128(base + kABytes);
-          const uint64_t db_hi = umma_desc_sw128(base + 2 * kABytes), db_lo = umma_desc_sw128(base + 2 * kABytes + n2 * kBK * 2);
+          const uint64_t da_hi = umma_desc(base), da_lo = umma_desc(base + kABytes);
+          const uint64_t db_hi = umma_desc(base + 2 * kABytes), db_lo = umma_desc(base + 2 * kABytes + n2 * kBK * 2);
           const uint32_t idesc2 = idesc_f16(n2);
           const uint32_t d2 = tmem_base + kAcc2Col + acc_col;
 #pragma unroll
@@ -263,7 +307,7 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     const int row_l = q * 32 + lane;        // row inside the tile = TMEM lane
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     int it = 0, tile_i = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_i) {
+    for (int t; (t = tile_of(blockIdx.x, tile_i, gridDim.x, m_tiles)) >= 0; ++tile_i) {
       const TileInfo ti = decode_tile(t, m_tiles);
       const int row = ti.m0 + row_l;
       const bool live = row < p.n_ctus;
@@ -275,9 +319,9 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         const int s = it % kStages;
         mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);   // the MMAs that last read this stage have retired
         uint8_t* st = smem + s * kStageBytes;
-        uint8_t* row_hi = st + (row_l >> 3) * 1024 + (row_l & 7) * 128;
+        uint8_t* row_hi = st + row_l * kRowBytes;
 #pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
+        for (int half = 0; half < kBK / 32; ++half) {
           uint32_t r[32];
           const int c0 = j * kBK + half * 32;
           tmem_ld_x32(tmem_base + lane_addr + c0, r);
@@ -290,7 +334,7 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             for (int i = 0; i < 8; ++i) o[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
           }
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {     // 4 chunks of 8 fp16 (16 bytes), swizzled: chunk ^= row % 8
+          for (int cc = 0; cc < 4; ++cc) {     // 16-byte chunks of 8 fp16; swizzle: chunk ^= row % 8 (128 B) | (row / 2) % 4 (64 B)
             uint32_t hw[4], lw[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -300,7 +344,7 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
               hw[e] = *reinterpret_cast<const uint32_t*>(&h);
               lw[e] = *reinterpret_cast<const uint32_t*>(&l);
             }
-            const int chunk = ((half * 4 + cc) ^ (row_l & 7)) * 16;
+            const int chunk = kBK == 64 ? ((half * 4 + cc) ^ (row_l & 7)) * 16 : (cc ^ ((row_l >> 1) & 3)) * 16;
             *reinterpret_cast<uint4*>(row_hi + chunk) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
             *reinterpret_cast<uint4*>(row_hi + kABytes + chunk) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
           }
@@ -417,7 +461,7 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// [rows][k_len] fp16 row-major (K contiguous) -> 2-D map, box 64 x box_rows, 128-byte swizzle.
+// [rows][k_len] fp16 row-major (K contiguous) -> 2-D map, box kBK x box_rows, swizzle span = one box row.
 bool make_kmajor_map(CUtensorMap* map, const __half* base, uint64_t k_len, uint64_t rows, uint32_t box_rows, const char** err) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) {
@@ -429,7 +473,7 @@ bool make_kmajor_map(CUtensorMap* map, const __half* base, uint64_t k_len, uint6
   cuuint32_t box[2] = {cuuint32_t(kBK), box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, kBK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     *err = "cuTensorMapEncodeTiled failed";
@@ -460,13 +504,13 @@ cudaError_t launch_fc_fused(const __half* feat_hi, const __half* feat_lo, const 
   if (p.n_ctus <= 0) return cudaSuccess;
   if (!w.valid) return cudaErrorInvalidValue;
   const int m_tiles = (p.n_ctus + kBM - 1) / kBM;
-  const int n_tiles = 2 * m_tiles;
   CUtensorMap map_a_hi, map_a_lo;
   const char* err = nullptr;
   if (!make_kmajor_map(&map_a_hi, feat_hi, kFeat, uint64_t(m_tiles) * kBM, kBM, &err) ||
       !make_kmajor_map(&map_a_lo, feat_lo, kFeat, uint64_t(m_tiles) * kBM, kBM, &err))
     return cudaErrorInvalidValue;
-  const int grid = n_tiles < sm_count ? n_tiles : sm_count;
+  const int n_tiles = 2 * m_tiles, even_sms = sm_count > 1 ? sm_count & ~1 : 2;
+  const int grid = n_tiles < even_sms ? n_tiles : even_sms;   // CTA pairs (tile_of)
   fc_fused_kernel<<<grid, kThreads, kSmemBytes, stream>>>(map_a_hi, map_a_lo, w.w1_hi_t0, w.w1_lo_t0, w.w1_hi_t1, w.w1_lo_t1,
                                                          w.w2_hi[0], w.w2_lo[0], w.w2_hi[1], w.w2_lo[1], w.w2_hi[2], w.w2_lo[2], p,
                                                          m_tiles);
