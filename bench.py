@@ -380,7 +380,8 @@ def run_ours(args):
             "config": {"workload": "config2: 1920x1080 4:2:0, 50 frames per rank per step, QP cycling 22/27/32/37",
                        "ctus_per_step": world * n_ctus, "sharding": "contiguous frame ranges, NCCL gather to rank 0" if world > 1 else "single GPU",
                        "l2": "inputs rotate over 4 clips (415 MB luma) + ~600 MB of scratch traffic per step, larger than the 126 MB L2",
-                       "dense_path": ("simt", "tcgen05 FC1 + heads kernel", "fused tcgen05 FC1+FC2+FC3")[net.query(3)]},
+                       "dense_path": ("simt", "tcgen05 FC1 + heads kernel", "fused tcgen05 FC1+FC2+FC3",
+                                      "fused tcgen05 FC1+FC2+FC3 on CTA pairs (cta_group::2)")[net.query(3)]},
             "e2e": {"value": e2e_value, "unit": "CTU/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": world * FRAMES * W * H, "d2h_bytes_per_step": world * n_ctus * 84,
                     "timing": "wall clock between device-synchronised barriers, max over ranks"},

@@ -136,8 +136,10 @@ struct ethcnn_handle {
   std::vector<std::unique_ptr<DeviceCtx>> devs;
   std::mutex mu;
   std::atomic<int64_t> launches{0};
-  int fc1_path = 2;  // 0 = SIMT fp32 FC1 + heads kernel, 1 = tcgen05 FC1 + heads kernel, 2 = fused tcgen05 FC1+FC2+FC3
-  size_t chunk_ctus = 148 * 128;
+  // 0 = SIMT fp32 FC1 + heads kernel, 1 = tcgen05 FC1 + heads kernel, 2 = fused tcgen05 FC1+FC2+FC3 (a CTA per tile),
+  // 3 = the fused kernel on CTA pairs (cta_group::2)
+  int fc1_path = 3;
+  size_t chunk_ctus = 148 * 256;   // 74 CTA pairs x 2 column tiles x 256 CTUs: four fused-FC tiles per pair, 16 conv groups per CTA
 };
 
 namespace ethcnn {
@@ -420,7 +422,7 @@ int run_device(ethcnn_handle* h, DeviceCtx& c, const uint8_t* d_y, int width, in
       ++h->launches;
       continue;
     }
-    if (h->fc1_path == 2) {  // FC1 + FC2 + FC3 in one tcgen05 kernel; a1 never leaves the SM
+    if (h->fc1_path >= 2) {  // FC1 + FC2 + FC3 in one tcgen05 kernel; a1 never leaves the SM
       FusedParams fp;
       const float q = scaled_qp(h->mode, qp);
       for (int i = 0; i < 336; ++i) fp.b2eff[i] = std::fmaf(q, m->h_w2q[i], m->h_b2[i]);
@@ -435,7 +437,7 @@ int run_device(ethcnn_handle* h, DeviceCtx& c, const uint8_t* d_y, int width, in
       fp.flags = gated ? c.flags : nullptr;
       fp.n_ctus = n, fp.ctu_begin = int(begin), fp.ctus_per_frame = ctus_per_frame, fp.chunks_per_frame = chunks_per_frame;
       StageTimer t(c, stream, ETHCNN_STAGE_FC1);
-      CUDA_TRY(launch_fc_fused(c.feat_hi, c.feat_lo, m->fused, fp, c.sm_count, stream));
+      CUDA_TRY(launch_fc_fused(c.feat_hi, c.feat_lo, m->fused, fp, h->fc1_path == 3 ? 2 : 1, c.sm_count, stream));
       ++h->launches;
       continue;
     }
@@ -861,7 +863,7 @@ int create_common(const char* model_dir, const char* thr_path, int mode, const s
     const long v = atol(e);
     if (v >= 1 && v <= (1 << 22)) h->chunk_ctus = size_t(v);
   }
-  if (const char* e = getenv("ETHCNN_FC1")) h->fc1_path = (strcmp(e, "simt") == 0) ? 0 : (strcmp(e, "tc") == 0 ? 1 : 2);
+  if (const char* e = getenv("ETHCNN_FC1")) h->fc1_path = (strcmp(e, "simt") == 0) ? 0 : (strcmp(e, "tc") == 0 ? 1 : (strcmp(e, "pair") == 0 ? 3 : 2));
   {
     const std::string tp = thr_path ? std::string(thr_path) : h->model_dir + "/Thr_info.txt";
     int rc = read_thresholds(tp, &h->t1, &h->t2);
@@ -1096,7 +1098,7 @@ int ethcnn_set_option(ethcnn_handle* h, int option, int64_t value) {
   std::lock_guard<std::mutex> lock(h->mu);
   switch (option) {
     case ETHCNN_OPT_FC1_PATH:
-      if (value < 0 || value > 2) return fail(ETHCNN_E_ARG, "FC path must be 0, 1 or 2");
+      if (value < 0 || value > 3) return fail(ETHCNN_E_ARG, "FC path must be 0, 1, 2 or 3");
       h->fc1_path = int(value);
       break;
     case ETHCNN_OPT_CHUNK_CTUS:

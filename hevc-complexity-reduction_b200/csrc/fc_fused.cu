@@ -36,15 +36,22 @@ namespace {
 constexpr int kBM = 128, kBK = ETHCNN_FC_BK;                 // K slice = one swizzle row: 64 fp16 (128 B) or 32 fp16 (64 B)
 static_assert(kBK == 64 || kBK == 32, "K slice must be one 128-byte or one 64-byte swizzle row");
 constexpr int kRowBytes = kBK * 2;
-constexpr int kStages = 192 * 1024 / (2 * kBM * kRowBytes + 2 * 256 * kRowBytes);   // 2 (K = 64) or 4 (K = 32)
 constexpr int kABytes = kBM * kRowBytes;                     // 16384 | 8192
-constexpr int kStageBytes = 2 * kABytes + 2 * 256 * kRowBytes; // 98304 | 49152
 constexpr int kKSteps = kFeat / kBK;                         // 42 | 84
 constexpr int kAcc2Col = 256;                                // TMEM column of accumulator 2
 constexpr int kThreads = 192;
 constexpr int kW3Floats = 48 * 1 + 96 * 4 + 192 * 16;        // 3504
 constexpr int kTableFloats = kW3Floats + 336 + 21 + kFc1 + 3; // w3 | b2eff | b3eff | b1 (padded to 16 B)
-constexpr int kSmemBytes = kStages * kStageBytes + kTableFloats * 4 + 256 + 1024;
+// kCtas = 1: one CTA per 128-CTU tile.  kCtas = 2: a CTA PAIR (cluster of two, tcgen05 cta_group::2) per 256-CTU tile;
+// each CTA stages its own 128 feature rows and HALF of the weight rows, so the weight traffic per CTU halves.
+template <int kCtas>
+struct Geo {
+  static constexpr int kBRowsMax = 256 / kCtas;                                   // weight rows a CTA stages per slice
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBRowsMax * kRowBytes;     // K = 64: 96 KB | 64 KB
+  static constexpr int kStages = 192 * 1024 / kStageBytes;                        // K = 64: 2 | 3
+  static constexpr int kSmemBytes = kStages * kStageBytes + kTableFloats * 4 + 256 + 1024;
+  static_assert((3 * kStages + 5) * 8 <= 256, "barrier block overflows its shared-memory slot");
+};
 
 // K-major operand tile in swizzled shared memory: rows of kBK fp16 (one swizzle row), 8-row groups back to back.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
@@ -57,21 +64,40 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   return d;
 }
 // kind::f16 instruction descriptor: D fp32, A = B = fp16, K-major both, M = 128, N as given.
+template <int kCtas>
 __device__ __forceinline__ uint32_t idesc_f16(int n) {
-  return (1u << 4) | (uint32_t(n >> 3) << 17) | (uint32_t(kBM >> 4) << 24);
+  return (1u << 4) | (uint32_t(n >> 3) << 17) | (uint32_t((kBM * kCtas) >> 4) << 24);
 }
+template <int kCtas>
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if (kCtas == 1)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
+// Arrive on `bar` when all MMAs issued so far by this thread have retired; for a pair, on that barrier in BOTH CTAs.
+template <int kCtas>
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  if (kCtas == 1)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(uint16_t(3))
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -108,14 +134,15 @@ struct TileInfo {
 // Static tile order: CTAs 2j and 2j+1 work on the SAME 128 CTUs at the same time, one on the head-16 columns and
 // one on the head-64/32 columns, and swap roles every iteration (type-1 tiles cost 4/3 of type-0 tiles).  The
 // feature slices of an M tile are therefore requested twice within a few microseconds and come from HBM once.
-__device__ __forceinline__ int tile_of(int cta, int iter, int n_ctas, int m_tiles) {
-  const int m = (cta >> 1) + (n_ctas >> 1) * iter;
-  return m < m_tiles ? 2 * m + ((cta ^ iter) & 1) : -1;
+// (A "unit" is a CTA, or a CTA pair; an M block is the 128 or 256 CTUs a unit covers.)
+__device__ __forceinline__ int tile_of(int unit, int iter, int n_units, int m_blocks) {
+  const int m = (unit >> 1) + (n_units >> 1) * iter;
+  return m < m_blocks ? 2 * m + ((unit ^ iter) & 1) : -1;
 }
-__device__ __forceinline__ TileInfo decode_tile(int t, int /*m_tiles*/) {
+__device__ __forceinline__ TileInfo decode_tile(int t, int rows_per_block, int row_ofs) {
   TileInfo ti;
   ti.type = t & 1;
-  ti.m0 = (t >> 1) * kBM;
+  ti.m0 = (t >> 1) * rows_per_block + row_ofs;
   ti.n0 = ti.type ? 192 : 0;
   ti.n1 = ti.type ? 256 : 192;
   ti.nslices = ti.n1 / kBK;
@@ -132,14 +159,31 @@ __device__ __forceinline__ void fc2_slice(int type, int j, int& head, int& kofs,
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
-fc_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                const __grid_constant__ CUtensorMap w1_hi_t0, const __grid_constant__ CUtensorMap w1_lo_t0,
-                const __grid_constant__ CUtensorMap w1_hi_t1, const __grid_constant__ CUtensorMap w1_lo_t1,
-                const __grid_constant__ CUtensorMap w2_hi_0, const __grid_constant__ CUtensorMap w2_lo_0,
-                const __grid_constant__ CUtensorMap w2_hi_1, const __grid_constant__ CUtensorMap w2_lo_1,
-                const __grid_constant__ CUtensorMap w2_hi_2, const __grid_constant__ CUtensorMap w2_lo_2,
-                const __grid_constant__ FusedParams p, const int m_tiles) {
+#define FC_FUSED_PARAMS                                                                                          \
+  const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,                    \
+      const __grid_constant__ CUtensorMap w1_hi_t0, const __grid_constant__ CUtensorMap w1_lo_t0,                \
+      const __grid_constant__ CUtensorMap w1_hi_t1, const __grid_constant__ CUtensorMap w1_lo_t1,                \
+      const __grid_constant__ CUtensorMap w2_hi_0, const __grid_constant__ CUtensorMap w2_lo_0,                  \
+      const __grid_constant__ CUtensorMap w2_hi_1, const __grid_constant__ CUtensorMap w2_lo_1,                  \
+      const __grid_constant__ CUtensorMap w2_hi_2, const __grid_constant__ CUtensorMap w2_lo_2,                  \
+      const __grid_constant__ FusedParams p, const int m_blocks
+#define FC_FUSED_ARGS \
+  map_a_hi, map_a_lo, w1_hi_t0, w1_lo_t0, w1_hi_t1, w1_lo_t1, w2_hi_0, w2_lo_0, w2_hi_1, w2_lo_1, w2_hi_2, w2_lo_2, p, m_blocks
+
+// Barriers.  In a pair, the MMAs are issued by the leader CTA (cluster rank 0) only, so everything the issuer waits
+// for -- full (TMA bytes of BOTH CTAs), a2_full, acc1_empty, acc2_empty (epilogue warps of both CTAs) -- lives in the
+// leader's shared memory and the peer arrives remotely; what the issuer signals -- empty, acc1_full, acc2_full -- is
+// committed to the same barrier in both CTAs (multicast commit).
+template <int kCtas>
+__device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const CUtensorMap& map_a_lo, const CUtensorMap& w1_hi_t0,
+                                              const CUtensorMap& w1_lo_t0, const CUtensorMap& w1_hi_t1, const CUtensorMap& w1_lo_t1,
+                                              const CUtensorMap& w2_hi_0, const CUtensorMap& w2_lo_0, const CUtensorMap& w2_hi_1,
+                                              const CUtensorMap& w2_lo_1, const CUtensorMap& w2_hi_2, const CUtensorMap& w2_lo_2,
+                                              const FusedParams& p, const int m_blocks) {
+  constexpr int kStages = Geo<kCtas>::kStages, kStageBytes = Geo<kCtas>::kStageBytes;
+  const uint32_t rank = kCtas == 2 ? cluster_ctarank() : 0u;   // 0 = leader
+  const int unit = blockIdx.x / kCtas, n_units = gridDim.x / kCtas;
+  const int row_ofs = int(rank) * kBM;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* tab = reinterpret_cast<float*>(smem + kStages * kStageBytes);
@@ -156,7 +200,20 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   uint64_t* acc2_full = acc1_full + 2;
   uint64_t* acc2_empty = acc1_full + 3;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc1_full + 4);
-  static_assert((3 * kStages + 5) * 8 <= 256, "barrier block overflows its shared-memory slot");
+  // cluster addresses of the leader's copies (identical shared-memory layout in both CTAs)
+  auto at_leader = [&](uint64_t* bar) -> uint32_t { return kCtas == 2 ? mapa_shared(smem_u32(bar), 0) : smem_u32(bar); };
+  auto arrive_at_leader = [&](uint64_t* bar) {
+    if (kCtas == 2) mbar_arrive_remote(mapa_shared(smem_u32(bar), 0));
+    else mbar_arrive(bar);
+  };
+  auto wait_shared = [&](uint64_t* bar, uint32_t parity) {   // a leader barrier both CTAs arrive on
+    if (kCtas == 2) mbar_wait_cluster(bar, parity);
+    else mbar_wait(bar, parity);
+  };
+  auto load_tile = [&](void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
+    if (kCtas == 2) tma_load_2d_pair(dst, map, at_leader(bar), x, y);
+    else tma_load_2d(dst, map, bar, x, y);
+  };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -168,16 +225,22 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a_hi), prefetch_tmap(&map_a_lo);
     prefetch_tmap(&w1_hi_t0), prefetch_tmap(&w1_lo_t0), prefetch_tmap(&w1_hi_t1), prefetch_tmap(&w1_lo_t1);
-    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 2), mbar_init(&empty[s], 1), mbar_init(&a2_full[s], 4);
-    mbar_init(acc1_full, 1), mbar_init(acc1_empty, 4), mbar_init(acc2_full, 1), mbar_init(acc2_empty, 4);
+    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 2), mbar_init(&empty[s], 1), mbar_init(&a2_full[s], 4 * kCtas);
+    mbar_init(acc1_full, 1), mbar_init(acc1_empty, 4 * kCtas), mbar_init(acc2_full, 1), mbar_init(acc2_empty, 4 * kCtas);
     mbar_fence_init();
   }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  if (warp == 1) {   // the same warp of both CTAs of a pair allocates collectively
+    if (kCtas == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (kCtas == 2) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -192,10 +255,12 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 #endif
     if (lane < 3) {
       int it = 0;
-      for (int iter = 0, t; (t = tile_of(blockIdx.x, iter, gridDim.x, m_tiles)) >= 0; ++iter) {
-        const TileInfo ti = decode_tile(t, m_tiles);
+      for (int iter = 0, t; (t = tile_of(unit, iter, n_units, m_blocks)) >= 0; ++iter) {
+        const TileInfo ti = decode_tile(t, kBM * kCtas, row_ofs);
         const CUtensorMap* wh = ti.type ? &w1_hi_t1 : &w1_hi_t0;
         const CUtensorMap* wl = ti.type ? &w1_lo_t1 : &w1_lo_t0;
+        const int nb = ti.n1 / kCtas;                 // weight rows this CTA stages
+        const int nrow = ti.n0 + int(rank) * nb;
         if (lane == 2) {
           for (int ks = 0; ks < ETHCNN_FC_L2_PREFETCH && ks < kKSteps; ++ks) {
             tma_prefetch_l2_2d(&map_a_hi, ks * kBK, ti.m0);
@@ -207,13 +272,13 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
           uint8_t* st = smem + s * kStageBytes;
           if (lane == 0) {
-            mbar_arrive_expect_tx(&full[s], 2 * kABytes);
-            tma_load_2d(st, &map_a_hi, &full[s], ks * kBK, ti.m0);
-            tma_load_2d(st + kABytes, &map_a_lo, &full[s], ks * kBK, ti.m0);
+            if (rank == 0) mbar_arrive_expect_tx(&full[s], kCtas * 2 * kABytes);
+            load_tile(st, &map_a_hi, &full[s], ks * kBK, ti.m0);
+            load_tile(st + kABytes, &map_a_lo, &full[s], ks * kBK, ti.m0);
           } else if (lane == 1) {
-            mbar_arrive_expect_tx(&full[s], 2 * ti.n1 * kBK * 2);
-            tma_load_2d(st + 2 * kABytes, wh, &full[s], ks * kBK, ti.n0);
-            tma_load_2d(st + 2 * kABytes + ti.n1 * kBK * 2, wl, &full[s], ks * kBK, ti.n0);
+            if (rank == 0) mbar_arrive_expect_tx(&full[s], kCtas * 2 * nb * kRowBytes);
+            load_tile(st + 2 * kABytes, wh, &full[s], ks * kBK, nrow);
+            load_tile(st + 2 * kABytes + nb * kRowBytes, wl, &full[s], ks * kBK, nrow);
           } else if (ks + ETHCNN_FC_L2_PREFETCH < kKSteps) {
             tma_prefetch_l2_2d(&map_a_hi, (ks + ETHCNN_FC_L2_PREFETCH) * kBK, ti.m0);
             tma_prefetch_l2_2d(&map_a_lo, (ks + ETHCNN_FC_L2_PREFETCH) * kBK, ti.m0);
@@ -225,26 +290,28 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           uint8_t* st = smem + s * kStageBytes;
           int head, kofs, n2, acc_col, first;
           fc2_slice(ti.type, j, head, kofs, n2, acc_col, first);
+          const int nb2 = n2 / kCtas;
           if (lane == 0) {
-            mbar_arrive(&full[s]);
+            if (rank == 0) mbar_arrive(&full[s]);
           } else if (lane == 1) {
             const CUtensorMap* bh = head == 0 ? &w2_hi_0 : (head == 1 ? &w2_hi_1 : &w2_hi_2);
             const CUtensorMap* bl = head == 0 ? &w2_lo_0 : (head == 1 ? &w2_lo_1 : &w2_lo_2);
-            mbar_arrive_expect_tx(&full[s], 2 * n2 * kBK * 2);
-            tma_load_2d(st + 2 * kABytes, bh, &full[s], kofs, 0);
-            tma_load_2d(st + 2 * kABytes + n2 * kBK * 2, bl, &full[s], kofs, 0);
+            if (rank == 0) mbar_arrive_expect_tx(&full[s], kCtas * 2 * nb2 * kRowBytes);
+            load_tile(st + 2 * kABytes, bh, &full[s], kofs, int(rank) * nb2);
+            load_tile(st + 2 * kABytes + nb2 * kRowBytes, bl, &full[s], kofs, int(rank) * nb2);
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer ------------------------------------------------
+    // ------------------------------------------------ MMA issuer (the leader CTA of a pair only) -------------------------
     int it = 0, tile_i = 0, a2_cnt[kStages] = {};
-    for (int t; (t = tile_of(blockIdx.x, tile_i, gridDim.x, m_tiles)) >= 0; ++tile_i) {
-      const TileInfo ti = decode_tile(t, m_tiles);
-      mbar_wait(acc1_empty, (tile_i & 1) ^ 1);
+    for (int t; rank == 0 && (t = tile_of(unit, tile_i, n_units, m_blocks)) >= 0; ++tile_i) {
+      const TileInfo ti = decode_tile(t, kBM * kCtas, row_ofs);
+      const int nb = ti.n1 / kCtas;
+      wait_shared(acc1_empty, (tile_i & 1) ^ 1);
       tc_fence_after();
-      const uint32_t idesc1 = idesc_f16(ti.n1);
+      const uint32_t idesc1 = idesc_f16<kCtas>(ti.n1);
       for (int ks = 0; ks < kKSteps; ++ks, ++it) {
         const int s = it % kStages;
         mbar_wait(&full[s], (it / kStages) & 1);
@@ -252,51 +319,45 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         if (lane == 0) {
           const uint32_t base = smem_u32(smem + s * kStageBytes);
           const uint64_t da_hi = umma_desc(base), da_lo = umma_desc(base + kABytes);
-          const uint64_t db_hi = umma_desc(base + 2 * kABytes), db_lo = umma_desc(base + 2 * kABytes + ti.n1 * kBK * 2);
-#ifdef ETHCNN_EXPERIMENT_NO_MMA   // measurement only: one MMA per stage instead of twelve
-          for (int k = 0; k < 1; ++k) {
-            umma_f16(tmem_base, da_hi, db_hi, idesc1, (ks | k) != 0);
-          }
-#else
+          const uint64_t db_hi = umma_desc(base + 2 * kABytes), db_lo = umma_desc(base + 2 * kABytes + nb * kRowBytes);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             const uint64_t adv = uint64_t(k * 32 >> 4);  // 16 fp16 = 32 bytes along K inside the swizzle atom
-            umma_f16(tmem_base, da_hi + adv, db_hi + adv, idesc1, (ks | k) != 0);
-            umma_f16(tmem_base, da_hi + adv, db_lo + adv, idesc1, 1);
-            umma_f16(tmem_base, da_lo + adv, db_hi + adv, idesc1, 1);
+            umma_f16<kCtas>(tmem_base, da_hi + adv, db_hi + adv, idesc1, (ks | k) != 0);
+            umma_f16<kCtas>(tmem_base, da_hi + adv, db_lo + adv, idesc1, 1);
+            umma_f16<kCtas>(tmem_base, da_lo + adv, db_hi + adv, idesc1, 1);
           }
-#endif
-          umma_commit(&empty[s]);
-          if (ks == kKSteps - 1) umma_commit(acc1_full);
+          umma_commit<kCtas>(&empty[s]);
+          if (ks == kKSteps - 1) umma_commit<kCtas>(acc1_full);
         }
         __syncwarp();
       }
       // FC2: A operand = this tile's a1 slices written by the epilogue warps into the ring
-      mbar_wait(acc2_empty, (tile_i & 1) ^ 1);
+      wait_shared(acc2_empty, (tile_i & 1) ^ 1);
       tc_fence_after();
       for (int j = 0; j < ti.nslices; ++j, ++it) {
         const int s = it % kStages;
         int head, kofs, n2, acc_col, first;
         fc2_slice(ti.type, j, head, kofs, n2, acc_col, first);
         mbar_wait(&full[s], (it / kStages) & 1);
-        mbar_wait(&a2_full[s], a2_cnt[s] & 1);
+        wait_shared(&a2_full[s], a2_cnt[s] & 1);
         ++a2_cnt[s];
         tc_fence_after();
         if (lane == 0) {
           const uint32_t base = smem_u32(smem + s * kStageBytes);
           const uint64_t da_hi = umma_desc(base), da_lo = umma_desc(base + kABytes);
-          const uint64_t db_hi = umma_desc(base + 2 * kABytes), db_lo = umma_desc(base + 2 * kABytes + n2 * kBK * 2);
-          const uint32_t idesc2 = idesc_f16(n2);
+          const uint64_t db_hi = umma_desc(base + 2 * kABytes), db_lo = umma_desc(base + 2 * kABytes + (n2 / kCtas) * kRowBytes);
+          const uint32_t idesc2 = idesc_f16<kCtas>(n2);
           const uint32_t d2 = tmem_base + kAcc2Col + acc_col;
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             const uint64_t adv = uint64_t(k * 32 >> 4);
-            umma_f16(d2, da_hi + adv, db_hi + adv, idesc2, (first && k == 0) ? 0u : 1u);
-            umma_f16(d2, da_hi + adv, db_lo + adv, idesc2, 1);
-            umma_f16(d2, da_lo + adv, db_hi + adv, idesc2, 1);
+            umma_f16<kCtas>(d2, da_hi + adv, db_hi + adv, idesc2, (first && k == 0) ? 0u : 1u);
+            umma_f16<kCtas>(d2, da_hi + adv, db_lo + adv, idesc2, 1);
+            umma_f16<kCtas>(d2, da_lo + adv, db_hi + adv, idesc2, 1);
           }
-          umma_commit(&empty[s]);
-          if (j == ti.nslices - 1) umma_commit(acc2_full);
+          umma_commit<kCtas>(&empty[s]);
+          if (j == ti.nslices - 1) umma_commit<kCtas>(acc2_full);
         }
         __syncwarp();
       }
@@ -307,8 +368,8 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     const int row_l = q * 32 + lane;        // row inside the tile = TMEM lane
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     int it = 0, tile_i = 0;
-    for (int t; (t = tile_of(blockIdx.x, tile_i, gridDim.x, m_tiles)) >= 0; ++tile_i) {
-      const TileInfo ti = decode_tile(t, m_tiles);
+    for (int t; (t = tile_of(unit, tile_i, n_units, m_blocks)) >= 0; ++tile_i) {
+      const TileInfo ti = decode_tile(t, kBM * kCtas, row_ofs);
       const int row = ti.m0 + row_l;
       const bool live = row < p.n_ctus;
       it += kKSteps;
@@ -349,13 +410,13 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             *reinterpret_cast<uint4*>(row_hi + kABytes + chunk) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
           }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA (async proxy)
+        asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes -> visible to the MMA (async proxy)
         __syncwarp();
-        if (lane == 0) mbar_arrive(&a2_full[s]);
+        if (lane == 0) arrive_at_leader(&a2_full[s]);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acc1_empty);
+      if (lane == 0) arrive_at_leader(acc1_empty);
 
       // ---- epi2: accumulator 2 -> a2 = leaky(acc * unscale2 + b2eff) -> FC3 -> sigmoid -> probabilities
       mbar_wait(acc2_full, tile_i & 1);
@@ -431,16 +492,23 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acc2_empty);
+      if (lane == 0) arrive_at_leader(acc2_empty);
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (kCtas == 2) cluster_sync_all();   // neither CTA leaves (or frees TMEM) while its peer still reads its shared memory / arrives on its barriers
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    if (kCtas == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) fc_fused_kernel(FC_FUSED_PARAMS) { fc_fused_body<1>(FC_FUSED_ARGS); }
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) fc_fused_pair_kernel(FC_FUSED_PARAMS) {
+  fc_fused_body<2>(FC_FUSED_ARGS);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -487,33 +555,51 @@ bool make_kmajor_map(CUtensorMap* map, const __half* base, uint64_t k_len, uint6
 bool fc_fused_prepare_weights(const __half* w1_hi, const __half* w1_lo, const __half* const w2_hi[3],
                               const __half* const w2_lo[3], FusedWeights* out, const char** err) {
   const int n1[3] = {64, 128, 256}, n2[3] = {48, 96, 192};
-  bool ok = make_kmajor_map(&out->w1_hi_t0, w1_hi, kFeat, kFc1, 192, err) && make_kmajor_map(&out->w1_lo_t0, w1_lo, kFeat, kFc1, 192, err) &&
-            make_kmajor_map(&out->w1_hi_t1, w1_hi, kFeat, kFc1, 256, err) && make_kmajor_map(&out->w1_lo_t1, w1_lo, kFeat, kFc1, 256, err);
-  for (int h = 0; ok && h < 3; ++h)
-    ok = make_kmajor_map(&out->w2_hi[h], w2_hi[h], n1[h], n2[h], n2[h], err) && make_kmajor_map(&out->w2_lo[h], w2_lo[h], n1[h], n2[h], n2[h], err);
+  bool ok = true;
+  for (int ctas = 1; ok && ctas <= 2; ++ctas) {   // box rows: what ONE CTA stages (all of the N rows, or half of them in a pair)
+    FusedWeights::Maps& m = out->maps[ctas - 1];
+    ok = make_kmajor_map(&m.w1_hi_t0, w1_hi, kFeat, kFc1, 192 / ctas, err) && make_kmajor_map(&m.w1_lo_t0, w1_lo, kFeat, kFc1, 192 / ctas, err) &&
+         make_kmajor_map(&m.w1_hi_t1, w1_hi, kFeat, kFc1, 256 / ctas, err) && make_kmajor_map(&m.w1_lo_t1, w1_lo, kFeat, kFc1, 256 / ctas, err);
+    for (int h = 0; ok && h < 3; ++h)
+      ok = make_kmajor_map(&m.w2_hi[h], w2_hi[h], n1[h], n2[h], n2[h] / ctas, err) &&
+           make_kmajor_map(&m.w2_lo[h], w2_lo[h], n1[h], n2[h], n2[h] / ctas, err);
+  }
   out->valid = ok;
   return ok;
 }
 
 cudaError_t fc_fused_configure() {
-  return cudaFuncSetAttribute(fc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(fc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<1>::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(fc_fused_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<2>::kSmemBytes);
 }
 
 cudaError_t launch_fc_fused(const __half* feat_hi, const __half* feat_lo, const FusedWeights& w, const FusedParams& p,
-                            int sm_count, cudaStream_t stream) {
+                            int ctas_per_tile, int sm_count, cudaStream_t stream) {
   if (p.n_ctus <= 0) return cudaSuccess;
-  if (!w.valid) return cudaErrorInvalidValue;
-  const int m_tiles = (p.n_ctus + kBM - 1) / kBM;
+  if (!w.valid || (ctas_per_tile != 1 && ctas_per_tile != 2)) return cudaErrorInvalidValue;
+  const int m_tiles = (p.n_ctus + kBM - 1) / kBM;            // rows the feature buffers hold (multiple of 128)
+  const int m_blocks = (m_tiles + ctas_per_tile - 1) / ctas_per_tile;
   CUtensorMap map_a_hi, map_a_lo;
   const char* err = nullptr;
+  // a pair's second half may lie past the last row: TMA zero-fills it and the epilogue skips those rows
   if (!make_kmajor_map(&map_a_hi, feat_hi, kFeat, uint64_t(m_tiles) * kBM, kBM, &err) ||
       !make_kmajor_map(&map_a_lo, feat_lo, kFeat, uint64_t(m_tiles) * kBM, kBM, &err))
     return cudaErrorInvalidValue;
-  const int n_tiles = 2 * m_tiles, even_sms = sm_count > 1 ? sm_count & ~1 : 2;
-  const int grid = n_tiles < even_sms ? n_tiles : even_sms;   // CTA pairs (tile_of)
-  fc_fused_kernel<<<grid, kThreads, kSmemBytes, stream>>>(map_a_hi, map_a_lo, w.w1_hi_t0, w.w1_lo_t0, w.w1_hi_t1, w.w1_lo_t1,
-                                                         w.w2_hi[0], w.w2_lo[0], w.w2_hi[1], w.w2_lo[1], w.w2_hi[2], w.w2_lo[2], p,
-                                                         m_tiles);
+  // units (CTAs or CTA pairs) work in twos on one M block (tile_of), so their number is even
+  const int n_tiles = 2 * m_blocks;
+  int units = (sm_count / ctas_per_tile) & ~1;
+  if (units < 2) units = 2;
+  if (units > n_tiles) units = n_tiles;
+  const FusedWeights::Maps& m = w.maps[ctas_per_tile - 1];
+  if (ctas_per_tile == 1)
+    fc_fused_kernel<<<units, kThreads, Geo<1>::kSmemBytes, stream>>>(map_a_hi, map_a_lo, m.w1_hi_t0, m.w1_lo_t0, m.w1_hi_t1, m.w1_lo_t1,
+                                                                    m.w2_hi[0], m.w2_lo[0], m.w2_hi[1], m.w2_lo[1], m.w2_hi[2], m.w2_lo[2],
+                                                                    p, m_blocks);
+  else
+    fc_fused_pair_kernel<<<2 * units, kThreads, Geo<2>::kSmemBytes, stream>>>(map_a_hi, map_a_lo, m.w1_hi_t0, m.w1_lo_t0, m.w1_hi_t1,
+                                                                            m.w1_lo_t1, m.w2_hi[0], m.w2_lo[0], m.w2_hi[1], m.w2_lo[1],
+                                                                            m.w2_hi[2], m.w2_lo[2], p, m_blocks);
   return cudaGetLastError();
 }
 

@@ -7,9 +7,12 @@
 namespace ethcnn {
 
 struct FusedWeights {
-  CUtensorMap w1_hi_t0, w1_lo_t0;  // [448][2688] fp16 K-major, box 64 x 192 (heads 64 + 32: rows 0..191)
-  CUtensorMap w1_hi_t1, w1_lo_t1;  // same tensor, box 64 x 256 (head 16: rows 192..447)
-  CUtensorMap w2_hi[3], w2_lo[3];  // per head [n2][n1] fp16 K-major, box 64 x n2
+  struct Maps {
+    CUtensorMap w1_hi_t0, w1_lo_t0;  // [448][2688] fp16 K-major, box K x 192 (heads 64 + 32: rows 0..191)
+    CUtensorMap w1_hi_t1, w1_lo_t1;  // same tensor, box K x 256 (head 16: rows 192..447)
+    CUtensorMap w2_hi[3], w2_lo[3];  // per head [n2][n1] fp16 K-major, box K x n2
+  };
+  Maps maps[2];                      // [0]: one CTA per tile; [1]: CTA pairs, each CTA stages half of the box rows
   bool valid = false;
 };
 
@@ -31,7 +34,8 @@ struct FusedParams {
 bool fc_fused_prepare_weights(const __half* w1_hi, const __half* w1_lo, const __half* const w2_hi[3],
                               const __half* const w2_lo[3], FusedWeights* out, const char** err);
 cudaError_t fc_fused_configure();
+// ctas_per_tile: 1 = a CTA per 128 CTUs; 2 = a CTA pair (tcgen05 cta_group::2) per 256 CTUs, half the weight traffic.
 cudaError_t launch_fc_fused(const __half* feat_hi, const __half* feat_lo, const FusedWeights& w, const FusedParams& p,
-                            int sm_count, cudaStream_t stream);
+                            int ctas_per_tile, int sm_count, cudaStream_t stream);
 
 }  // namespace ethcnn

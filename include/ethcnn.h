@@ -130,7 +130,7 @@ int ethcnn_decisions(ethcnn_handle* h, const float* prob, size_t n_ctus, const f
 /* Introspection (for bench.py and tests). */
 #define ETHCNN_Q_KERNEL_LAUNCHES   1 /* kernels launched by this handle since creation            */
 #define ETHCNN_Q_N_DEVICES         2
-#define ETHCNN_Q_FC1_PATH          3 /* dense path: 2 = fused tcgen05 FC1+FC2+FC3, 1 = tcgen05 FC1, 0 = SIMT */
+#define ETHCNN_Q_FC1_PATH          3 /* dense path, see ETHCNN_OPT_FC1_PATH                           */
 #define ETHCNN_Q_TMA_LOADER_USED   4 /* 1 if the last device call used the TMA tile loader         */
 #define ETHCNN_Q_SM_COUNT          5
 int ethcnn_query(ethcnn_handle* h, int what, int64_t* value);
@@ -148,7 +148,8 @@ int ethcnn_profile_read(ethcnn_handle* h, int stage, double* ms_total, int64_t* 
 
 /* Tuning knobs (before the first predict call): see ETHCNN_OPT_*. */
 #define ETHCNN_OPT_FC1_PATH    1 /* 0 = SIMT fp32 FC1 + heads kernel, 1 = tcgen05 FC1 + heads kernel,
-                                    2 = fused tcgen05 FC1+FC2+FC3 (default) */
+                                    2 = fused tcgen05 FC1+FC2+FC3, one CTA per 128 CTUs,
+                                    3 = the fused kernel on CTA pairs (tcgen05 cta_group::2, 256 CTUs per pair) */
 #define ETHCNN_OPT_CHUNK_CTUS  2 /* CTUs per feature-buffer chunk                    */
 int ethcnn_set_option(ethcnn_handle* h, int option, int64_t value);
 

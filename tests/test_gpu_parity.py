@@ -74,7 +74,7 @@ def test_reference_vectors_ldp(eb, ldp_model_dir, golden_dir):
         assert np.abs(fc1 - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
 
 
-@pytest.mark.parametrize("fc1_path", [2, 1, 0])
+@pytest.mark.parametrize("fc1_path", [3, 2, 1, 0])
 @pytest.mark.parametrize("seed", [1, 2])
 def test_synthetic_weights_vs_oracle(eb, tmp_path, fc1_path, seed):
     """Random checkpoints in the reference's 36-tensor layout: a layout/ordering mistake cannot hide behind
@@ -118,9 +118,13 @@ def test_chunking_and_loader_variants_are_bit_identical(eb, ai_model_dir):
     yuv = np.frombuffer(eo.synth_yuv(W, H, nf, seed0=5), np.uint8)
     with eb.EthCnn(d, None, eb.MODE_AI, device=0) as net:
         base = net.predict_yuv_buffer(yuv, W, H, qp)
-        net.set_option(2, 100)                # chunk boundary inside frames and inside tile groups
-        assert np.array_equal(net.predict_yuv_buffer(yuv, W, H, qp), base)
-        net.set_option(2, 148 * 128)
+        for chunk in (100, 300):              # chunk boundary inside frames and inside tile groups; 300: the second CTA pair's
+            net.set_option(2, chunk)          # second half lies wholly past the chunk (TMA zero fill)
+            assert np.array_equal(net.predict_yuv_buffer(yuv, W, H, qp), base)
+            net.set_option(1, 2)              # one CTA per tile instead of CTA pairs: same arithmetic
+            assert np.abs(net.predict_yuv_buffer(yuv, W, H, qp) - base).max() <= 1e-6
+            net.set_option(1, 3)
+        net.set_option(2, 148 * 256)
         # device entry point: TMA loader (aligned pitch) vs plain-load loader (pitch = W, not 16-aligned)
         luma = np.stack([yuv.reshape(nf, -1)[k, :W * H].reshape(H, W) for k in range(nf)])
         out = torch.empty((nf * 72, 21), dtype=torch.float32, device="cuda")
@@ -147,6 +151,9 @@ def test_repeatability_and_frame_independence(net):
     c = net.predict_yuv_buffer(rev, W, H, qp).reshape(nf, -1, 21)[::-1].reshape(-1, 21)
     assert np.array_equal(a, c)
     assert a.shape == (nf * 510, 21) and np.isfinite(a).all() and a.min() >= 0 and a.max() <= 1
+    # 80 frames = 40 800 CTUs: more than one feature-buffer chunk (37 888 CTUs), boundary inside a frame
+    big = net.predict_yuv_buffer(np.tile(yuv, 20), W, H, qp).reshape(20, nf * 510, 21)
+    assert all(np.array_equal(big[k], a) for k in range(20))
 
 
 def test_full_size_config2_and_config3_frames_vs_oracle(net):
