@@ -74,51 +74,57 @@ __device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ah)[4], con
   mma16816(d, al, bh);
 }
 
-// (s0, s1) -> packed fp16 hi pair and lo pair with hi + lo == s to ~22 bits
-__device__ __forceinline__ void split2(float s0, float s1, uint32_t& hi, uint32_t& lo) {
-  const __half2 h = __floats2half2_rn(s0, s1);
-  const __half2 l = __floats2half2_rn(s0 - __low2float(h), s1 - __high2float(h));
+// Packed fp32 pair arithmetic (sm_100 FFMA2 / FMUL2 / FADD2): the accumulator pairs of an mma.sync C fragment sit in
+// adjacent registers, so bias, leaky and the hi/lo split are done two values at a time.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("{\n.reg .b64 ra, rb, rc, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmov.b64 rc, {%6, %7};\n"
+      "fma.rn.f32x2 rd, ra, rb, rc;\nmov.b64 {%0, %1}, rd;\n}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 r;
+  asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmul.rn.f32x2 rd, ra, rb;\nmov.b64 {%0, %1}, rd;\n}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  float2 r;
+  asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nsub.rn.f32x2 rd, ra, rb;\nmov.b64 {%0, %1}, rd;\n}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+
+// One accumulator pair -> leaky(d * u + b) -> packed fp16 hi pair and lo pair with hi + lo == value to ~22 bits.
+__device__ __forceinline__ void act_split(float d0, float d1, float2 u, float2 b, uint32_t& hi, uint32_t& lo) {
+  const float2 t = fma2(make_float2(d0, d1), u, b);
+  const float2 m = mul2(t, make_float2(0.2f, 0.2f));
+  const float2 r = make_float2(fmaxf(m.x, t.x), fmaxf(m.y, t.y));   // Maximum(alpha*x, x)
+  const __half2 h = __floats2half2_rn(r.x, r.y);
+  const float2 l = sub2(r, make_float2(__low2float(h), __high2float(h)));
+  const __half2 lh = __floats2half2_rn(l.x, l.y);
   hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
+  lo = *reinterpret_cast<const uint32_t*>(&lh);
 }
 
-// Integer sum of a quad's pixel block ((16 pool) x (16 pool) pixels at shared address blk, row pitch 64):
-// lane d adds pooled rows d, d+4, d+8, d+12; the caller reduces over the quad.
-__device__ __forceinline__ uint32_t block_rows_sum(int pool, uint32_t blk, int d) {
-  uint32_t s = 0;
-  const int chunks = pool;  // 16-byte chunks per pixel row
-#pragma unroll 1
-  for (int r = d; r < 16; r += 4) {
-#pragma unroll 1
-    for (int a = 0; a < pool; ++a) {
-      const uint32_t row = blk + (pool * r + a) * kCtu;
-#pragma unroll 1
-      for (int k = 0; k < chunks; ++k) {
-        const uint4 v = lds_u128(row + 16 * k);
-        s = __dp4a(v.x, 0x01010101u, s);
-        s = __dp4a(v.y, 0x01010101u, s);
-        s = __dp4a(v.z, 0x01010101u, s);
-        s = __dp4a(v.w, 0x01010101u, s);
-      }
-    }
-  }
-  return s;
+__device__ __forceinline__ uint32_t centred_half2(uint32_t biased_bits, float centre) {
+  // biased_bits: two fp16 bit patterns 0x6400 + n = 1024 + n (n < 1024); subtract 1024 + centre: exact
+  const __half2 c = __floats2half2_rn(centre, centre);
+  const __half2 v = __hsub2(*reinterpret_cast<const __half2*>(&biased_bits), c);
+  return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-// conv1 A operand of region pair T of a quad: for patch p, register reg = rx + 2*ki holds the pooled pair
-// (y = 8T + 4(p/2) + d/2 + 2ki, x = 8rx + 4(p%2) + 2(d%2) + {0,1}) as exact fp16 hi/lo of (256 s - W) / 32.
-__device__ __forceinline__ void cvt_pair(int s0, int s1, float wneg, uint32_t& hi, uint32_t& lo) {
-  // (256 s - W) / 32 = 8 s - W / 32, exact in fp32 (|.| < 2^16 with 5 fractional bits); wneg = -W / 32
-  const float f0 = fmaf(__int2float_rn(s0), 8.0f, wneg), f1 = fmaf(__int2float_rn(s1), 8.0f, wneg);
-  const __half2 h = __floats2half2_rn(f0, f1);
-  const __half2 l = __floats2half2_rn(f0 - __low2float(h), f1 - __high2float(h));
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-}
-
+// conv1 A operand of region pair T of a quad: for patch p = 2 ph + pl, register reg = rx + 2 ki holds the pooled pair
+// (y = 8T + 4 ph + d/2 + 2 ki, x = 8 rx + 4 pl + 2 (d%2) + {0,1}) as s - 128 pool^2, s = integer sum of the pool x pool
+// pixels: an integer of magnitude <= 2048, i.e. EXACT in fp16 -- conv1 needs no lo part for its A operand, and the mean
+// removal (a per-window constant) moves into the bias: conv(s - mean) = conv(s - centre) + (centre - mean) * sum(taps).
 template <int P>
-__device__ __forceinline__ void load_x_p(uint32_t blk, int T, int d, float wsum, uint32_t (&xh)[16], uint32_t (&xl)[16]) {
-  const int ky0 = d >> 1, xs = 2 * (d & 1);
+__device__ __forceinline__ void load_x_p(uint32_t blk, int T, int d, uint32_t (&xh)[16]) {
+  const int ky0 = d >> 1, e = d & 1;
 #pragma unroll
   for (int ph = 0; ph < 2; ++ph)
 #pragma unroll
@@ -127,50 +133,54 @@ __device__ __forceinline__ void load_x_p(uint32_t blk, int T, int d, float wsum,
       if (P == 1) {
         const uint4 row = lds_u128(blk + y * kCtu);
         const uint32_t w[4] = {row.x, row.y, row.z, row.w};
+        const uint32_t sel = e ? 0x4342u : 0x4140u;   // bytes (2e, 2e+1) -> low bytes of the two halves, 0x64 above: 1024 + pixel
 #pragma unroll
         for (int pl = 0; pl < 2; ++pl)
 #pragma unroll
-          for (int rx = 0; rx < 2; ++rx) {
-            const uint32_t hw = (w[2 * rx + pl] >> (8 * xs)) & 0xffffu;
-            cvt_pair(int(hw & 0xffu), int(hw >> 8), wsum, xh[4 * (2 * ph + pl) + rx + 2 * ki], xl[4 * (2 * ph + pl) + rx + 2 * ki]);
-          }
+          for (int rx = 0; rx < 2; ++rx)
+            xh[4 * (2 * ph + pl) + rx + 2 * ki] = centred_half2(__byte_perm(w[2 * rx + pl], 0x64646464u, sel), 1024.f + 128.f);
       } else {
 #pragma unroll
         for (int pl = 0; pl < 2; ++pl)
 #pragma unroll
           for (int rx = 0; rx < 2; ++rx) {
-            const int x0 = 8 * rx + 4 * pl + xs;
-            uint32_t s0 = 0, s1 = 0;
+            const int x0 = 8 * rx + 4 * pl + 2 * e;
+            uint32_t v;
             if (P == 2) {
               const uint32_t a = lds_u32(blk + (2 * y) * kCtu + 2 * x0), b = lds_u32(blk + (2 * y + 1) * kCtu + 2 * x0);
-              s0 = __dp4a(b, 0x00000101u, __dp4a(a, 0x00000101u, 0u));
-              s1 = __dp4a(b, 0x01010000u, __dp4a(a, 0x01010000u, 0u));
+              const uint32_t s0 = __dp4a(b, 0x00000101u, __dp4a(a, 0x00000101u, 0x6400u));   // 0x6400 + s: fp16 bits of 1024 + s
+              const uint32_t s1 = __dp4a(b, 0x01010000u, __dp4a(a, 0x01010000u, 0x6400u));
+              v = centred_half2(__byte_perm(s0, s1, 0x5410u), 1024.f + 512.f);
             } else {
+              uint32_t s0 = 0u - 2048u, s1 = 0u - 2048u;
 #pragma unroll
               for (int a = 0; a < 4; ++a) {
-                const uint2 v = lds_u64(blk + (4 * y + a) * kCtu + 4 * x0);
-                s0 = __dp4a(v.x, 0x01010101u, s0);
-                s1 = __dp4a(v.y, 0x01010101u, s1);
+                const uint2 q = lds_u64(blk + (4 * y + a) * kCtu + 4 * x0);
+                s0 = __dp4a(q.x, 0x01010101u, s0);
+                s1 = __dp4a(q.y, 0x01010101u, s1);
               }
+              const __half2 h = __floats2half2_rn(__int2float_rn(int(s0)), __int2float_rn(int(s1)));
+              v = *reinterpret_cast<const uint32_t*>(&h);
             }
-            cvt_pair(int(s0), int(s1), wsum, xh[4 * (2 * ph + pl) + rx + 2 * ki], xl[4 * (2 * ph + pl) + rx + 2 * ki]);
+            xh[4 * (2 * ph + pl) + rx + 2 * ki] = v;
           }
       }
     }
 }
 
-__device__ __forceinline__ void load_x(int pool, uint32_t blk, int T, int d, float wsum, uint32_t (&xh)[16], uint32_t (&xl)[16]) {
+__device__ __forceinline__ void load_x(int pool, uint32_t blk, int T, int d, uint32_t (&xh)[16]) {
   if (pool == 1) {
-    load_x_p<1>(blk, T, d, wsum, xh, xl);
+    load_x_p<1>(blk, T, d, xh);
   } else if (pool == 2) {
-    load_x_p<2>(blk, T, d, wsum, xh, xl);
+    load_x_p<2>(blk, T, d, xh);
   } else {
-    load_x_p<4>(blk, T, d, wsum, xh, xl);
+    load_x_p<4>(blk, T, d, xh);
   }
 }
 
 struct QuadSet {        // what a lane needs to know about its quad in set A or B
   uint32_t blk;         // shared-memory address of the quad's pixel block inside its CTU tile
+  uint32_t wsum;        // shared-memory address of this lane's share of the quad's window sum (block-sum table)
   __half* hi;           // feature rows of the quad's CTU (global memory)
   __half* lo;
   int c2_off;           // offset of the 24 conv2 features of region 0 of the quad
@@ -186,11 +196,14 @@ __device__ __noinline__ void warp_task(const int pool, const uint32_t wb, const 
   const int d = lane & 3;
   // leaky(v) * 2^e == leaky(v * 2^e): the power-of-two operand scales are folded into the unscale factors and biases
   const float sc1 = lds_f32(wb + 4 * (kHdrOff + 3));
-  const float u1 = lds_f32(wb + 4 * kHdrOff) * cst * sc1;
-  const float u2 = lds_f32(wb + 4 * (kHdrOff + 1)) * fscale, u3 = lds_f32(wb + 4 * (kHdrOff + 2)) * fscale;
+  const float u1 = lds_f32(wb + 4 * kHdrOff) * cst * sc1;     // per unit of sum((256 s - W) / 32 * B)
+  const float2 u1x8 = make_float2(8.f * u1, 8.f * u1);         // per unit of sum((s - centre) * B)
+  const float u2s = lds_f32(wb + 4 * (kHdrOff + 1)) * fscale, u3s = lds_f32(wb + 4 * (kHdrOff + 2)) * fscale;
+  const float2 u2 = make_float2(u2s, u2s), u3 = make_float2(u3s, u3s), fs2 = make_float2(fscale, fscale);
   // this lane's output channels: conv1 {2d, 2d+1, 8+2d, 9+2d}; conv2 / conv3 {8 nt + 2d, +1}
-  float2 b1lo = lds_f32x2(wb + 4 * (kB1Off + 2 * d)), b1hi = lds_f32x2(wb + 4 * (kB1Off + 8 + 2 * d));
-  b1lo.x *= sc1, b1lo.y *= sc1, b1hi.x *= sc1, b1hi.y *= sc1;
+  const float2 b1lo = mul2(lds_f32x2(wb + 4 * (kB1Off + 2 * d)), make_float2(sc1, sc1));
+  const float2 b1hi = mul2(lds_f32x2(wb + 4 * (kB1Off + 8 + 2 * d)), make_float2(sc1, sc1));
+  const float2 t1lo = lds_f32x2(wb + 4 * (kW1SumOff + 2 * d)), t1hi = lds_f32x2(wb + 4 * (kW1SumOff + 8 + 2 * d));
   uint2 f1h[2], f1l[2];
 #pragma unroll
   for (int nt = 0; nt < 2; ++nt) {
@@ -203,7 +216,7 @@ __device__ __noinline__ void warp_task(const int pool, const uint32_t wb, const 
   uint32_t keep_h[6], keep_l[6];   // set A's conv2 outputs of the current region pair, waiting for set B's
 #pragma unroll
   for (int i = 0; i < 6; ++i) keep_h[i] = keep_l[i] = 0u;
-  float wneg_a = 0.f, wneg_b = 0.f;
+  float2 ba_lo = b1lo, ba_hi = b1hi, bb_lo = b1lo, bb_hi = b1hi;   // conv1 bias + mean term of the quad, sets A / B
 
   // (region pair T, set st) = (it / 2, it % 2); rolled so that the loop body stays inside the instruction cache
 #pragma unroll 1
@@ -215,35 +228,47 @@ __device__ __noinline__ void warp_task(const int pool, const uint32_t wb, const 
     const int c2_off = st ? qb.c2_off : qa.c2_off;
     const bool valid = st ? qb.valid : qa.valid;
     if (T == 0) {
-      // integer sum over the quad's 16x16 pooled window (256 pool^2 pixels), kept as -W/32 (exact)
-      uint32_t ws = block_rows_sum(pool, blk, d);
-      ws += __shfl_xor_sync(0xffffffffu, ws, 1);
-      ws += __shfl_xor_sync(0xffffffffu, ws, 2);
-      const float w = -__uint2float_rn(ws) * 0.03125f;
-      if (st) wneg_b = w; else wneg_a = w;
+      // W = integer sum over the quad's 16x16 pooled window (256 pool^2 pixels) from the 16x16-pixel block sums the
+      // producer warp tabulated; the mean term (centre - W/256) * 256/32 = 8 centre - W/32 is exact in fp32
+      uint32_t ws;
+      if (pool == 4) {
+        const uint4 v = lds_u128(st ? qb.wsum : qa.wsum);
+        ws = v.x + v.y + v.z + v.w;
+      } else {
+        ws = lds_u32(st ? qb.wsum : qa.wsum);
+      }
+      if (pool != 1) {
+        ws += __shfl_xor_sync(0xffffffffu, ws, 1);
+        ws += __shfl_xor_sync(0xffffffffu, ws, 2);
+      }
+      const float mu = fmaf(__uint2float_rn(ws), -0.03125f, float(1024 * pool * pool)) * u1;
+      const float2 mu2 = make_float2(mu, mu);
+      const float2 lo2 = fma2(mu2, t1lo, b1lo), hi2 = fma2(mu2, t1hi, b1hi);
+      if (st) bb_lo = lo2, bb_hi = hi2; else ba_lo = lo2, ba_hi = hi2;
     }
-    uint32_t xh[16], xl[16];
-    load_x(pool, blk, T, d, st ? wneg_b : wneg_a, xh, xl);
+    const float2 be_lo = st ? bb_lo : ba_lo, be_hi = st ? bb_hi : ba_hi;
+    uint32_t xh[16];
+    load_x(pool, blk, T, d, xh);
     float d2[3][4];
 #pragma unroll
     for (int nt = 0; nt < 3; ++nt) d2[nt][0] = d2[nt][1] = d2[nt][2] = d2[nt][3] = 0.f;
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-      // conv1 for patch p of regions 2T (row g) and 2T+1 (row g+8)
-      const uint32_t a1h[4] = {xh[4 * p], xh[4 * p + 1], xh[4 * p + 2], xh[4 * p + 3]};
-      const uint32_t a1l[4] = {xl[4 * p], xl[4 * p + 1], xl[4 * p + 2], xl[4 * p + 3]};
+      // conv1 for patch p of regions 2T (row g) and 2T+1 (row g+8): the A operand is exact, two passes (B hi, B lo)
+      const uint32_t a1[4] = {xh[4 * p], xh[4 * p + 1], xh[4 * p + 2], xh[4 * p + 3]};
       float d1[2][4];
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) {
         d1[nt][0] = d1[nt][1] = d1[nt][2] = d1[nt][3] = 0.f;
-        mma3(d1[nt], a1h, a1l, f1h[nt], f1l[nt]);
+        mma16816(d1[nt], a1, f1h[nt]);
+        mma16816(d1[nt], a1, f1l[nt]);
       }
       // bias + leaky + re-split: the C fragments become the conv2 A fragment of k-step p
       uint32_t a2h[4], a2l[4];
-      split2(leaky(fmaf(d1[0][0], u1, b1lo.x)), leaky(fmaf(d1[0][1], u1, b1lo.y)), a2h[0], a2l[0]);
-      split2(leaky(fmaf(d1[0][2], u1, b1lo.x)), leaky(fmaf(d1[0][3], u1, b1lo.y)), a2h[1], a2l[1]);
-      split2(leaky(fmaf(d1[1][0], u1, b1hi.x)), leaky(fmaf(d1[1][1], u1, b1hi.y)), a2h[2], a2l[2]);
-      split2(leaky(fmaf(d1[1][2], u1, b1hi.x)), leaky(fmaf(d1[1][3], u1, b1hi.y)), a2h[3], a2l[3]);
+      act_split(d1[0][0], d1[0][1], u1x8, be_lo, a2h[0], a2l[0]);
+      act_split(d1[0][2], d1[0][3], u1x8, be_lo, a2h[1], a2l[1]);
+      act_split(d1[1][0], d1[1][1], u1x8, be_hi, a2h[2], a2l[2]);
+      act_split(d1[1][2], d1[1][3], u1x8, be_hi, a2h[3], a2l[3]);
 #pragma unroll
       for (int nt = 0; nt < 3; ++nt) {
         const uint2 wh = lds_u64(wb + 4 * kF2HiOff + ((p * 3 + nt) * 32 + lane) * 8);
@@ -255,10 +280,9 @@ __device__ __noinline__ void warp_task(const int pool, const uint32_t wb, const 
     uint32_t cur_h[6], cur_l[6];   // pair index 3 (r - 2T) + nt
 #pragma unroll
     for (int nt = 0; nt < 3; ++nt) {
-      float2 b2 = lds_f32x2(wb + 4 * (kB2Off + 8 * nt + 2 * d));
-      b2.x *= fscale, b2.y *= fscale;
-      split2(leaky(fmaf(d2[nt][0], u2, b2.x)), leaky(fmaf(d2[nt][1], u2, b2.y)), cur_h[nt], cur_l[nt]);
-      split2(leaky(fmaf(d2[nt][2], u2, b2.x)), leaky(fmaf(d2[nt][3], u2, b2.y)), cur_h[3 + nt], cur_l[3 + nt]);
+      const float2 b2 = mul2(lds_f32x2(wb + 4 * (kB2Off + 8 * nt + 2 * d)), fs2);
+      act_split(d2[nt][0], d2[nt][1], u2, b2, cur_h[nt], cur_l[nt]);
+      act_split(d2[nt][2], d2[nt][3], u2, b2, cur_h[3 + nt], cur_l[3 + nt]);
       if (valid) {
         const int o = c2_off + T * g24 + 8 * nt + 2 * d;
         *reinterpret_cast<uint32_t*>(hi + o) = cur_h[nt];
@@ -289,11 +313,10 @@ __device__ __noinline__ void warp_task(const int pool, const uint32_t wb, const 
 
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
-    float2 b3 = lds_f32x2(wb + 4 * (kB3Off + 8 * nt + 2 * d));
-    b3.x *= fscale, b3.y *= fscale;
+    const float2 b3 = mul2(lds_f32x2(wb + 4 * (kB3Off + 8 * nt + 2 * d)), fs2);
     uint32_t h0, l0, h1, l1;
-    split2(leaky(fmaf(d3[nt][0], u3, b3.x)), leaky(fmaf(d3[nt][1], u3, b3.y)), h0, l0);
-    split2(leaky(fmaf(d3[nt][2], u3, b3.x)), leaky(fmaf(d3[nt][3], u3, b3.y)), h1, l1);
+    act_split(d3[nt][0], d3[nt][1], u3, b3, h0, l0);
+    act_split(d3[nt][2], d3[nt][3], u3, b3, h1, l1);
     if (qa.valid) {
       *reinterpret_cast<uint32_t*>(qa.hi + qa.c3_off + 8 * nt + 2 * d) = h0;
       *reinterpret_cast<uint32_t*>(qa.lo + qa.c3_off + 8 * nt + 2 * d) = l0;
@@ -308,7 +331,8 @@ __device__ __noinline__ void warp_task(const int pool, const uint32_t wb, const 
 constexpr int kTileBytes = kCtu * kCtu;                       // 4096
 constexpr int kStageBytes = kGroupCtus * kTileBytes;          // 65536
 constexpr int kWeightBytes = ((kConvFloats * 4 + 127) / 128) * 128;
-constexpr int kConvSmemBytes = kWeightBytes + kConvStages * kStageBytes + 2 * kConvStages * 8 + 128;
+constexpr int kSumWords = kGroupCtus * 16;                   // 16x16-pixel block sums of a group: [ctu][4 qy + qx]
+constexpr int kConvSmemBytes = kWeightBytes + kConvStages * (kStageBytes + kSumWords * 4) + 3 * kConvStages * 8 + 128;
 
 template <bool kTma>
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -316,8 +340,10 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
   extern __shared__ __align__(128) uint8_t smem[];
   float* wsm = reinterpret_cast<float*>(smem);
   uint8_t* tiles = smem + kWeightBytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + kConvStages * kStageBytes);
-  uint64_t* empty = full + kConvStages;
+  uint32_t* sums = reinterpret_cast<uint32_t*>(tiles + kConvStages * kStageBytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sums + kConvStages * kSumWords);   // tile bytes landed
+  uint64_t* empty = full + kConvStages;                                           // all warp tasks of the group done
+  uint64_t* ready = empty + kConvStages;                                          // block sums of the group tabulated
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   {
@@ -329,6 +355,7 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
     for (int s = 0; s < kConvStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], kGroupTasks);
+      mbar_init(&ready[s], 1);
     }
     mbar_fence_init();
   }
@@ -337,7 +364,7 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
   const int n_groups = (p.n_ctus + kGroupCtus - 1) / kGroupCtus;
 
   if (warp == 0) {
-    // ---------------- producer: stream tile groups into the ring ----------------
+    // ---------------- producer: stream tile groups into the ring, tabulate their 16x16 block sums ----------------
     for (int j = 0;; ++j) {
       const int g = blockIdx.x + j * gridDim.x;
       if (g >= n_groups) break;
@@ -371,6 +398,32 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[stage]);
       }
+      // Integer sums of the 16 blocks of 16x16 pixels of every tile: the mean-removal windows of the three branches
+      // are 1, 4 and 16 of these blocks.  Lane l reads the 16-byte chunk l%4 of row 8 jj + l/4: 512 contiguous
+      // bytes per instruction, conflict-free; the compute warps are busy with the previous group meanwhile.
+      mbar_wait(&full[stage], parity);
+      const uint32_t t0 = smem_u32(dst) + (lane >> 2) * kCtu + (lane & 3) * 16;
+      uint32_t* sm = sums + stage * kSumWords;
+      for (int c = 0; c < nv; ++c) {
+        uint32_t acc[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const uint4 v = lds_u128(t0 + c * kTileBytes + jj * 8 * kCtu);
+          acc[jj >> 1] = __dp4a(v.w, 0x01010101u, __dp4a(v.z, 0x01010101u, __dp4a(v.y, 0x01010101u, __dp4a(v.x, 0x01010101u, acc[jj >> 1]))));
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 4);
+          acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 8);
+          acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 16);
+        }
+        if (lane < 4) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) sm[c * 16 + q * 4 + lane] = acc[q];
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ready[stage]);
     }
   } else {
     // ---------------- compute warps: warp tasks round-robin ----------------
@@ -384,7 +437,10 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
       const int stage = j % kConvStages;
       const uint32_t parity = (j / kConvStages) & 1;
       mbar_wait(&full[stage], parity);
+      mbar_wait(&ready[stage], parity);
       const uint32_t tile0 = smem_u32(tiles + stage * kStageBytes);
+      const uint32_t sum0 = smem_u32(sums + stage * kSumWords);
+      const int d = lane & 3;
       const int ctu0 = grp * kGroupCtus;  // index inside this launch
       // lane group g owns quad (qy, qx) of CTU ca (set A) and of CTU cb / quad row qy + 2 (set B)
       int pool, br, ca, cb, qy_a, qy_b, qx, rg, qg, c2_base, c3_base;
@@ -404,6 +460,11 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
       const size_t row_a = size_t(qa.valid ? ctu0 + ca : 0) * kFeat, row_b = size_t(qb.valid ? ctu0 + cb : 0) * kFeat;
       qa.blk = tile0 + ca * kTileBytes + (bpx * qy_a) * kCtu + bpx * qx;
       qb.blk = tile0 + cb * kTileBytes + (bpx * qy_b) * kCtu + bpx * qx;
+      // this lane's share of the window sum: S = the quad's own block; M = block (2 qy + d/2, 2 qx + d%2) of the quad's
+      // 2x2 blocks; L = block row d (four blocks, one 16-byte load) of the CTU's 4x4
+      const int sa = pool == 1 ? 4 * qy_a + qx : (pool == 2 ? (2 * qy_a + (d >> 1)) * 4 + 2 * qx + (d & 1) : 4 * d);
+      const int sb = pool == 1 ? 4 * qy_b + qx : (pool == 2 ? (2 * qy_b + (d >> 1)) * 4 + 2 * qx + (d & 1) : 4 * d);
+      qa.wsum = sum0 + 4 * (ca * 16 + sa), qb.wsum = sum0 + 4 * (cb * 16 + sb);
       qa.hi = p.feat_hi + row_a, qa.lo = p.feat_lo + row_a;
       qb.hi = p.feat_hi + row_b, qb.lo = p.feat_lo + row_b;
       qa.c2_off = c2_base + ((2 * qy_a) * rg + 2 * qx) * 24, qb.c2_off = c2_base + ((2 * qy_b) * rg + 2 * qx) * 24;

@@ -36,7 +36,8 @@ constexpr int kF2HiOff = 352;    // conv2:  4 k-steps x 3 n-tiles
 constexpr int kF2LoOff = 1120;
 constexpr int kF3HiOff = 1888;   // conv3:  6 k-steps x 4 n-tiles
 constexpr int kF3LoOff = 3424;
-constexpr int kConvBranchFloats = 4960;
+constexpr int kW1SumOff = 4960;  // [16] floats: per conv1 output channel, the sum over the 16 taps of (hi + lo) as stored above
+constexpr int kConvBranchFloats = 4976;
 constexpr int kConvFloats = 3 * kConvBranchFloats;  // branch order S, M, L
 
 // conv-stage tiling

@@ -144,6 +144,18 @@ bool pack_model(const std::map<std::string, BundleTensor>& t, float input_bound,
           }
     };
     pack_frags(w1->data, 16, 1, 2, e1w, kF1HiOff, kF1LoOff);
+    // per output channel: sum over the taps of the conv1 filter AS STORED (hi + lo); the kernel feeds conv1 with
+    // centred integer samples and adds (centre - window mean) * this sum to the bias instead of subtracting the mean
+    for (int co = 0; co < 16; ++co) {
+      double s = 0;
+      const float sc = std::ldexp(1.0f, e1w);
+      for (int k = 0; k < 16; ++k) {
+        const float v = w1->data[size_t(k) * 16 + co] * sc;
+        const float h = f16_bits_to_f32(f32_to_f16_bits(v));
+        s += double(h) + double(f16_bits_to_f32(f32_to_f16_bits(v - h)));
+      }
+      dst[kW1SumOff + co] = float(s);
+    }
     pack_frags(w2->data, 24, 4, 3, e2w, kF2HiOff, kF2LoOff);
     pack_frags(w3->data, 32, 6, 4, e3w, kF3HiOff, kF3LoOff);
   }

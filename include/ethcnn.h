@@ -159,7 +159,7 @@ void ethcnn_free_pinned(void* p);
 
 /* Host-side testing hooks (no GPU needed): the checkpoint reader + weight packer and the Thr_info.txt
  * parser, exposed so the CPU test-suite can check them against the oracle.
- *   conv     3 * 4960 32-bit words (branch S, M, L blocks in the shared-memory layout of csrc/kernels.h:
+ *   conv     3 * 4976 32-bit words (branch S, M, L blocks in the shared-memory layout of csrc/kernels.h:
  *            header, biases, filters as mma.sync B fragments in fp16 hi/lo)
  *   w1       2688 * 448 floats (heads 64 | 32 | 16 side by side), b1 448 floats
  *   w1_hi/lo 448 * 2688 fp16 bit patterns of w1 * 2^exps[1] (K-major)

@@ -12,7 +12,7 @@ import numpy as np
 kOffC3S, kOffC3M, kOffC3L, kOffC2S, kOffC2M, kOffC2L = 0, 512, 640, 672, 2208, 2592
 # conv block of one branch in 32-bit words (csrc/kernels.h)
 kHdrOff, kB1Off, kB2Off, kB3Off = 0, 16, 32, 56
-kF1HiOff, kF1LoOff, kF2HiOff, kF2LoOff, kF3HiOff, kF3LoOff, kBranchWords = 96, 224, 352, 1120, 1888, 3424, 4960
+kF1HiOff, kF1LoOff, kF2HiOff, kF2LoOff, kF3HiOff, kF3LoOff, kW1SumOff, kBranchWords = 96, 224, 352, 1120, 1888, 3424, 4960, 4976
 F = np.float32
 
 
@@ -72,9 +72,23 @@ def task_lane_info(task, lane):
 
 
 def conv_features_group(tiles, conv_words, exps, cst3):
-    """tiles [16,64,64] uint8; conv_words [3][4960] uint32 (the packed conv blocks); exps [3][4] = per branch
+    """tiles [16,64,64] uint8; conv_words [3][4976] uint32 (the packed conv blocks); exps [3][4] = per branch
     (e1w, e_c1, e2w, e3w); cst3 = input_scale / (256 pool^2) per branch.  Returns float [16, 2688]."""
     feat = np.full((16, 2688), np.nan)
+    # the producer warp's table: integer sums of the 16 blocks of 16x16 pixels of every tile, [ctu][4 qy + qx];
+    # lane l adds chunk l%4 (16 bytes) of rows 8 jj + l/4, jj -> block row jj/2, then the 8 lanes of a chunk are reduced
+    sums = np.zeros((16, 16), np.int64)
+    for c in range(16):
+        acc = np.zeros((32, 4), np.int64)
+        for lane in range(32):
+            for jj in range(8):
+                row, ch = 8 * jj + (lane >> 2), lane & 3
+                acc[lane, jj >> 1] += int(tiles[c][row, 16 * ch:16 * ch + 16].astype(np.int64).sum())
+        for sh in (4, 8, 16):
+            acc = acc + acc[np.arange(32) ^ sh]
+        for lane in range(4):
+            for q in range(4):
+                sums[c, q * 4 + lane] = acc[lane, q]
     for task in range(21):
         info = [task_lane_info(task, lane) for lane in range(32)]
         P, br, G, QG = info[0][0], info[0][1], info[0][2], info[0][3]
@@ -83,19 +97,27 @@ def conv_features_group(tiles, conv_words, exps, cst3):
         bias = blk.view(np.float32)
         b1, b2, b3 = bias[kB1Off:kB1Off + 16], bias[kB2Off:kB2Off + 24], bias[kB3Off:kB3Off + 32]
         f1 = unpack_frags(blk, kF1HiOff, kF1LoOff, 2, e1w)           # [nt]
+        w1sum = bias[kW1SumOff:kW1SumOff + 16].astype(np.float64) / 2.0 ** e1w   # per channel: sum over the 16 taps
         f2 = unpack_frags(blk, kF2HiOff, kF2LoOff, 12, e2w)          # [p*3 + nt]
         f3 = unpack_frags(blk, kF3HiOff, kF3LoOff, 24, e3w)          # [j*4 + nt]
         pairs = np.zeros((2, 32, 12, 2))                              # conv3 A operand: [set][lane][s = 3r + nt][e]
         for st in range(2):
-            # ---- window sum over the quad's 16x16 pooled block: lane d sums pooled rows d, d+4, d+8, d+12
+            # ---- window sum over the quad's 16x16 pooled block from the block-sum table: S = the quad's own block,
+            # M = lane d takes block (2 qy + d/2, 2 qx + d%2), L = lane d takes block row d; M / L reduce over d
             wsum = np.zeros(32, np.int64)
             for lane in range(32):
                 c, qy, qx = info[lane][4][st]
                 d = lane & 3
-                blkpx = tiles[c][16 * P * qy:16 * P * (qy + 1), 16 * P * qx:16 * P * (qx + 1)].astype(np.int64)
-                wsum[lane] = sum(blkpx[P * r:P * (r + 1)].sum() for r in (d, d + 4, d + 8, d + 12))
-            wsum = wsum + wsum[np.arange(32) ^ 1]
-            wsum = wsum + wsum[np.arange(32) ^ 2]
+                if P == 1:
+                    wsum[lane] = sums[c, 4 * qy + qx]
+                elif P == 2:
+                    wsum[lane] = sums[c, (2 * qy + (d >> 1)) * 4 + 2 * qx + (d & 1)]
+                else:
+                    wsum[lane] = sums[c, 4 * d:4 * d + 4].sum()
+            if P != 1:
+                wsum = wsum + wsum[np.arange(32) ^ 1]
+                wsum = wsum + wsum[np.arange(32) ^ 2]
+            centre = 128 * P * P
             for T in range(2):
                 D2 = np.zeros((3, 32, 4))
                 for p in range(4):
@@ -111,7 +133,7 @@ def conv_features_group(tiles, conv_words, exps, cst3):
                             y = 8 * T + 4 * (p >> 1) + ky
                             for e in range(2):
                                 x = 8 * rx + 4 * (p & 1) + 2 * (d & 1) + e
-                                a1[lane, reg, e] = float(256 * pooled[y, x] - wsum[lane]) * cst3[br]
+                                a1[lane, reg, e] = float(pooled[y, x] - centre)      # exact in fp16: |.| <= 2048
                     a2 = np.zeros((32, 4, 2))
                     for nt in range(2):
                         D1 = mma_m16n8k16(a1, f1[nt], np.zeros((32, 4)))
@@ -120,7 +142,9 @@ def conv_features_group(tiles, conv_words, exps, cst3):
                             for i in range(4):
                                 ch = 8 * nt + 2 * d + (i & 1)
                                 # conv2 A fragment regs: [0] row g lo cols, [1] row g+8 lo cols, [2] row g hi cols, [3] row g+8 hi cols
-                                a2[lane, 2 * nt + (i >> 1), i & 1] = leaky(D1[lane, i] + b1[ch])
+                                # conv(256 s - W) = 256 conv(s - centre) + (256 centre - W) * sum(taps)
+                                pre = 256 * cst3[br] * D1[lane, i] + float(256 * centre - wsum[lane]) * cst3[br] * w1sum[ch]
+                                a2[lane, 2 * nt + (i >> 1), i & 1] = leaky(pre + b1[ch])
                     for nt in range(3):
                         D2[nt] = mma_m16n8k16(a2, f2[p * 3 + nt], D2[nt])
                 for nt in range(3):
@@ -177,7 +201,7 @@ def fc1_three_pass(feat, w1_hi_bits, w1_lo_bits, b1, feat_exp, w_exp):
 
 def pack_conv_block_reference(w, branch_base, input_bound):
     """Python statement of the conv block layout model.cpp must produce for one branch (used to check the C++
-    packer): returns (words uint32[4960], (e1w, e_c1, e2w, e3w))."""
+    packer): returns (words uint32[4976], (e1w, e_c1, e2w, e3w))."""
     def v(i):
         return w["Variable" if branch_base + i == 0 else "Variable_%d" % (branch_base + i)]
     w1, b1, w2, b2, w3, b3 = v(0).reshape(16, 16), v(1), v(2).reshape(64, 24), v(3), v(4).reshape(96, 32), v(5)
@@ -208,6 +232,10 @@ def pack_conv_block_reference(w, branch_base, input_bound):
         words[off_hi:off_hi + n] = hi.reshape(-1).view(np.uint32)
         words[off_lo:off_lo + n] = lo.reshape(-1).view(np.uint32)
     frags(w1, 1, 2, e1w, kF1HiOff, kF1LoOff)
+    s1 = (w1.astype(np.float32) * np.float32(2.0 ** e1w)).astype(np.float32)
+    h1 = s1.astype(np.float16)
+    l1 = (s1 - h1.astype(np.float32)).astype(np.float16)
+    fl[kW1SumOff:kW1SumOff + 16] = (h1.astype(np.float64) + l1.astype(np.float64)).sum(0).astype(np.float32)
     frags(w2, 4, 3, e2w, kF2HiOff, kF2LoOff)
     frags(w3, 6, 4, e3w, kF3HiOff, kF3LoOff)
     return words, (e1w, e_c1, e2w, e3w)

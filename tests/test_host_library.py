@@ -45,7 +45,7 @@ def test_missing_library_fails_loudly(eb, monkeypatch, tmp_path):
 
 def _pack(eb, prefix, input_bound=1.0):
     lib = eb.load_library()
-    conv = np.zeros(3 * 4960, np.uint32)
+    conv = np.zeros(3 * 4976, np.uint32)
     w1 = np.zeros((2688, 448), np.float32)
     b1 = np.zeros(448, np.float32)
     hi = np.zeros((448, 2688), np.uint16)
@@ -54,7 +54,7 @@ def _pack(eb, prefix, input_bound=1.0):
     fb = np.zeros(1, np.float32)
     rc = lib.ethcnn_debug_pack_model(prefix.encode(), C.c_float(input_bound), *[C.c_void_p(a.ctypes.data) for a in
                                                                                    (conv, w1, b1, hi, lo, exps, fb)])
-    return rc, conv.reshape(3, 4960), w1, b1, hi, lo, exps, float(fb[0])
+    return rc, conv.reshape(3, 4976), w1, b1, hi, lo, exps, float(fb[0])
 
 
 @pytest.mark.parametrize("which", ["real", "synthetic"])

@@ -12,7 +12,7 @@ from oracle import ethcnn_oracle as eo
 
 def _packed(eb, prefix, bound):
     lib = eb.load_library()
-    conv = np.zeros(3 * 4960, np.uint32)
+    conv = np.zeros(3 * 4976, np.uint32)
     b1 = np.zeros(448, np.float32)
     hi = np.zeros((448, 2688), np.uint16)
     lo = np.zeros((448, 2688), np.uint16)
@@ -21,7 +21,7 @@ def _packed(eb, prefix, bound):
                                      C.c_void_p(b1.ctypes.data), C.c_void_p(hi.ctypes.data), C.c_void_p(lo.ctypes.data),
                                      C.c_void_p(exps.ctypes.data), None)
     assert rc == 0
-    return conv.reshape(3, 4960), b1, hi, lo, exps
+    return conv.reshape(3, 4976), b1, hi, lo, exps
 
 
 @pytest.mark.parametrize("mode", [eo.MODE_AI, eo.MODE_LDP])
