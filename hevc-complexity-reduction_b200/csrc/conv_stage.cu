@@ -38,7 +38,6 @@
 namespace ethcnn {
 namespace {
 
-__device__ __forceinline__ float leaky(float v) { return fmaxf(0.2f * v, v); }  // Maximum(alpha*x, x), alpha = 0.2
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   uint32_t v;
@@ -185,13 +184,12 @@ struct QuadSet {        // what a lane needs to know about its quad in set A or 
   __half* lo;
   int c2_off;           // offset of the 24 conv2 features of region 0 of the quad
   int c3_off;           // offset of the quad's 32 conv3 features
-  bool valid;           // CTU exists (tail groups run with masked stores)
 };
 
 // One warp task: the conv stack for 16 quads (8 per set).
 //   pool   1 / 2 / 4 (warp-uniform)    wb  shared-memory byte address of the branch's weight block
 //   g24    feature distance between vertically adjacent regions (regions per row * 24)
-__device__ __noinline__ void warp_task(const int pool, const uint32_t wb, const float cst, const float fscale, const int lane,
+__device__ __forceinline__ void warp_task(const int pool, const uint32_t wb, const float cst, const float fscale, const int lane,
                                        const QuadSet qa, const QuadSet qb, const int g24) {
   const int d = lane & 3;
   // leaky(v) * 2^e == leaky(v * 2^e): the power-of-two operand scales are folded into the unscale factors and biases
@@ -226,7 +224,6 @@ __device__ __noinline__ void warp_task(const int pool, const uint32_t wb, const 
     __half* const hi = st ? qb.hi : qa.hi;
     __half* const lo = st ? qb.lo : qa.lo;
     const int c2_off = st ? qb.c2_off : qa.c2_off;
-    const bool valid = st ? qb.valid : qa.valid;
     if (T == 0) {
       // W = integer sum over the quad's 16x16 pooled window (256 pool^2 pixels) from the 16x16-pixel block sums the
       // producer warp tabulated; the mean term (centre - W/256) * 256/32 = 8 centre - W/32 is exact in fp32
@@ -283,13 +280,11 @@ __device__ __noinline__ void warp_task(const int pool, const uint32_t wb, const 
       const float2 b2 = mul2(lds_f32x2(wb + 4 * (kB2Off + 8 * nt + 2 * d)), fs2);
       act_split(d2[nt][0], d2[nt][1], u2, b2, cur_h[nt], cur_l[nt]);
       act_split(d2[nt][2], d2[nt][3], u2, b2, cur_h[3 + nt], cur_l[3 + nt]);
-      if (valid) {
-        const int o = c2_off + T * g24 + 8 * nt + 2 * d;
-        *reinterpret_cast<uint32_t*>(hi + o) = cur_h[nt];
-        *reinterpret_cast<uint32_t*>(lo + o) = cur_l[nt];
-        *reinterpret_cast<uint32_t*>(hi + o + 24) = cur_h[3 + nt];
-        *reinterpret_cast<uint32_t*>(lo + o + 24) = cur_l[3 + nt];
-      }
+      const int o = c2_off + T * g24 + 8 * nt + 2 * d;
+      *reinterpret_cast<uint32_t*>(hi + o) = cur_h[nt];
+      *reinterpret_cast<uint32_t*>(lo + o) = cur_l[nt];
+      *reinterpret_cast<uint32_t*>(hi + o + 24) = cur_h[3 + nt];
+      *reinterpret_cast<uint32_t*>(lo + o + 24) = cur_l[3 + nt];
     }
     if (st == 0) {
 #pragma unroll
@@ -317,14 +312,10 @@ __device__ __noinline__ void warp_task(const int pool, const uint32_t wb, const 
     uint32_t h0, l0, h1, l1;
     act_split(d3[nt][0], d3[nt][1], u3, b3, h0, l0);
     act_split(d3[nt][2], d3[nt][3], u3, b3, h1, l1);
-    if (qa.valid) {
-      *reinterpret_cast<uint32_t*>(qa.hi + qa.c3_off + 8 * nt + 2 * d) = h0;
-      *reinterpret_cast<uint32_t*>(qa.lo + qa.c3_off + 8 * nt + 2 * d) = l0;
-    }
-    if (qb.valid) {
-      *reinterpret_cast<uint32_t*>(qb.hi + qb.c3_off + 8 * nt + 2 * d) = h1;
-      *reinterpret_cast<uint32_t*>(qb.lo + qb.c3_off + 8 * nt + 2 * d) = l1;
-    }
+    *reinterpret_cast<uint32_t*>(qa.hi + qa.c3_off + 8 * nt + 2 * d) = h0;
+    *reinterpret_cast<uint32_t*>(qa.lo + qa.c3_off + 8 * nt + 2 * d) = l0;
+    *reinterpret_cast<uint32_t*>(qb.hi + qb.c3_off + 8 * nt + 2 * d) = h1;
+    *reinterpret_cast<uint32_t*>(qb.lo + qb.c3_off + 8 * nt + 2 * d) = l1;
   }
 }
 
@@ -370,7 +361,7 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
       if (g >= n_groups) break;
       const int stage = j % kConvStages;
       const uint32_t parity = (j / kConvStages) & 1;
-      mbar_wait(&empty[stage], parity ^ 1);
+      mbar_wait_relaxed(&empty[stage], parity ^ 1);   // a whole group period away: do not compete for issue slots
       const int nv = min(kGroupCtus, p.n_ctus - g * kGroupCtus);
       uint8_t* dst = tiles + stage * kStageBytes;
       if (kTma) {
@@ -456,8 +447,9 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
       }
       const int bpx = 16 * pool;  // quad block edge in pixels
       QuadSet qa, qb;
-      qa.valid = (ctu0 + ca) < p.n_ctus, qb.valid = (ctu0 + cb) < p.n_ctus;
-      const size_t row_a = size_t(qa.valid ? ctu0 + ca : 0) * kFeat, row_b = size_t(qb.valid ? ctu0 + cb : 0) * kFeat;
+      // CTUs past the end of a tail group are computed on stale tile bytes and stored to the dump row
+      const size_t row_a = size_t((ctu0 + ca) < p.n_ctus ? ctu0 + ca : p.dump_row) * kFeat;
+      const size_t row_b = size_t((ctu0 + cb) < p.n_ctus ? ctu0 + cb : p.dump_row) * kFeat;
       qa.blk = tile0 + ca * kTileBytes + (bpx * qy_a) * kCtu + bpx * qx;
       qb.blk = tile0 + cb * kTileBytes + (bpx * qy_b) * kCtu + bpx * qx;
       // this lane's share of the window sum: S = the quad's own block; M = block (2 qy + d/2, 2 qx + d%2) of the quad's

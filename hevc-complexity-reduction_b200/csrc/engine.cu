@@ -279,8 +279,9 @@ int ensure_scratch(ethcnn_handle* h, DeviceCtx& c, size_t flags_needed) {
     c.chunk_ctus = h->chunk_ctus;
     // rows are padded to a multiple of 128 so the FC1 tile loads never leave the allocation
     const size_t rows = (c.chunk_ctus + 127) / 128 * 128;
-    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c.feat_hi), rows * kFeat * 2));
-    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c.feat_lo), rows * kFeat * 2));
+    // + 1: the dump row of the conv stage (ConvLaunch::dump_row)
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c.feat_hi), (rows + 1) * kFeat * 2));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c.feat_lo), (rows + 1) * kFeat * 2));
     CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c.fc1), rows * kFc1 * 4));
     CUDA_TRY(cudaMemset(c.feat_hi, 0, rows * kFeat * 2));
     CUDA_TRY(cudaMemset(c.feat_lo, 0, rows * kFeat * 2));
@@ -384,6 +385,7 @@ int run_device(ethcnn_handle* h, DeviceCtx& c, const uint8_t* d_y, int width, in
     cl.convw = m->conv;
     cl.feat_hi = c.feat_hi, cl.feat_lo = c.feat_lo;
     cl.n_ctus = n, cl.ctu_begin = int(begin), cl.ctus_per_row = ctu_cols, cl.ctus_per_frame = ctus_per_frame;
+    cl.dump_row = int((c.chunk_ctus + 127) / 128 * 128);
     cl.cst[0] = in_scale / 256.0f, cl.cst[1] = in_scale / 1024.0f, cl.cst[2] = in_scale / 4096.0f;
     cl.feat_scale = std::ldexp(1.0f, m->feat_exp);
     c.last_feat_exp = m->feat_exp;

@@ -55,6 +55,7 @@ struct ConvLaunch {
   __half* feat_hi;           // device [n_ctus][kFeat], value * feat_scale rounded to fp16
   __half* feat_lo;           // device [n_ctus][kFeat], residual of the above
   int n_ctus;                // CTUs in this launch
+  int dump_row;              // a feature row nobody reads (stores of a tail group's absent CTUs go there)
   int ctu_begin;             // global index (frame-major raster) of the first CTU of this launch
   int ctus_per_row;
   int ctus_per_frame;

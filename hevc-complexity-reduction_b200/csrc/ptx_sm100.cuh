@@ -41,6 +41,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// For waits that are known to be long (a producer waiting for its ring slot): sleep between polls so that the
+// waiting warp does not take issue slots from the warps doing the work.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(256);
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+
 // --- thread-block clusters / CTA pairs (tcgen05 cta_group::2) ---
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
