@@ -146,7 +146,8 @@ __device__ __forceinline__ void load_x_p(uint32_t blk, int T, int d, uint32_t (&
             const int x0 = 8 * rx + 4 * pl + 2 * e;
             uint32_t v;
             if (P == 2) {
-              const uint32_t a = lds_u32(blk + (2 * y) * kCtu + 2 * x0), b = lds_u32(blk + (2 * y + 1) * kCtu + 2 * x0);
+              // the two pixel rows in lane-dependent order (the sum is symmetric): lanes d/2 = 0, 1 hit different banks
+              const uint32_t a = lds_u32(blk + (2 * y + ky0) * kCtu + 2 * x0), b = lds_u32(blk + (2 * y + (ky0 ^ 1)) * kCtu + 2 * x0);
               const uint32_t s0 = __dp4a(b, 0x00000101u, __dp4a(a, 0x00000101u, 0x6400u));   // 0x6400 + s: fp16 bits of 1024 + s
               const uint32_t s1 = __dp4a(b, 0x01010000u, __dp4a(a, 0x01010000u, 0x6400u));
               v = centred_half2(__byte_perm(s0, s1, 0x5410u), 1024.f + 512.f);
@@ -320,7 +321,8 @@ __device__ __forceinline__ void warp_task(const int pool, const uint32_t wb, con
 }
 
 constexpr int kTileBytes = kCtu * kCtu;                       // 4096
-constexpr int kStageBytes = kGroupCtus * kTileBytes;          // 65536
+constexpr int kTileStride = kTileBytes;                       // (TMA needs 128-byte aligned destinations: no bank skew between tiles)
+constexpr int kStageBytes = kGroupCtus * kTileStride;         // 65536
 constexpr int kWeightBytes = ((kConvFloats * 4 + 127) / 128) * 128;
 constexpr int kSumWords = kGroupCtus * 16;                   // 16x16-pixel block sums of a group: [ctu][4 qy + qx]
 constexpr int kConvSmemBytes = kWeightBytes + kConvStages * (kStageBytes + kSumWords * 4) + 3 * kConvStages * 8 + 128;
@@ -371,7 +373,7 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
           const int n = p.ctu_begin + g * kGroupCtus + lane;
           const int f = n / p.ctus_per_frame, r = n - f * p.ctus_per_frame;
           const int cy = r / p.ctus_per_row, cx = r - cy * p.ctus_per_row;
-          tma_load_3d(dst + lane * kTileBytes, &tmap, &full[stage], cx * kCtu, cy * kCtu, f);
+          tma_load_3d(dst + lane * kTileStride, &tmap, &full[stage], cx * kCtu, cy * kCtu, f);
         }
       } else {
         for (int c = 0; c < nv; ++c) {
@@ -380,7 +382,7 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
           const int cy = r / p.ctus_per_row, cx = r - cy * p.ctus_per_row;
           const uint8_t* src = p.luma + size_t(f) * p.frame_stride + size_t(cy) * kCtu * p.pitch + size_t(cx) * kCtu;
           const int rows = min(kCtu, p.height - cy * kCtu), cols = min(kCtu, p.width - cx * kCtu);
-          uint8_t* t = dst + c * kTileBytes;
+          uint8_t* t = dst + c * kTileStride;
           for (int i = lane; i < kTileBytes; i += 32) {
             const int y = i >> 6, x = i & 63;
             t[i] = (y < rows && x < cols) ? src[size_t(y) * p.pitch + x] : uint8_t(0);  // zero padding
@@ -399,7 +401,7 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
         uint32_t acc[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
-          const uint4 v = lds_u128(t0 + c * kTileBytes + jj * 8 * kCtu);
+          const uint4 v = lds_u128(t0 + c * kTileStride + jj * 8 * kCtu);
           acc[jj >> 1] = __dp4a(v.w, 0x01010101u, __dp4a(v.z, 0x01010101u, __dp4a(v.y, 0x01010101u, __dp4a(v.x, 0x01010101u, acc[jj >> 1]))));
         }
 #pragma unroll
@@ -422,7 +424,8 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
     const uint32_t wsm_addr = smem_u32(wsm);
     const int g = lane >> 2;
     for (int t = cw;; t += kConvComputeWarps) {
-      const int j = t / kGroupTasks, task = t - j * kGroupTasks;
+      // the four M and the L task of a group take longest (pooling on the fly): they go first, the 16 S tasks fill up
+      const int j = t / kGroupTasks, task = (t - j * kGroupTasks + 16) % kGroupTasks;
       const int grp = blockIdx.x + j * gridDim.x;
       if (grp >= n_groups) break;
       const int stage = j % kConvStages;
@@ -450,8 +453,8 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
       // CTUs past the end of a tail group are computed on stale tile bytes and stored to the dump row
       const size_t row_a = size_t((ctu0 + ca) < p.n_ctus ? ctu0 + ca : p.dump_row) * kFeat;
       const size_t row_b = size_t((ctu0 + cb) < p.n_ctus ? ctu0 + cb : p.dump_row) * kFeat;
-      qa.blk = tile0 + ca * kTileBytes + (bpx * qy_a) * kCtu + bpx * qx;
-      qb.blk = tile0 + cb * kTileBytes + (bpx * qy_b) * kCtu + bpx * qx;
+      qa.blk = tile0 + ca * kTileStride + (bpx * qy_a) * kCtu + bpx * qx;
+      qb.blk = tile0 + cb * kTileStride + (bpx * qy_b) * kCtu + bpx * qx;
       // this lane's share of the window sum: S = the quad's own block; M = block (2 qy + d/2, 2 qx + d%2) of the quad's
       // 2x2 blocks; L = block row d (four blocks, one 16-byte load) of the CTU's 4x4
       const int sa = pool == 1 ? 4 * qy_a + qx : (pool == 2 ? (2 * qy_a + (d >> 1)) * 4 + 2 * qx + (d & 1) : 4 * d);
@@ -461,6 +464,12 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
       qb.hi = p.feat_hi + row_b, qb.lo = p.feat_lo + row_b;
       qa.c2_off = c2_base + ((2 * qy_a) * rg + 2 * qx) * 24, qb.c2_off = c2_base + ((2 * qy_b) * rg + 2 * qx) * 24;
       qa.c3_off = c3_base + (qy_a * qg + qx) * 32, qb.c3_off = c3_base + (qy_b * qg + qx) * 32;
+#ifdef ETHCNN_EXPERIMENT_S_ONLY
+      if (task < 16)
+#endif
+#ifdef ETHCNN_EXPERIMENT_ML_ONLY
+      if (task >= 16)
+#endif
       warp_task(pool, wsm_addr + 4 * br * kConvBranchFloats, p.cst[br], p.feat_scale, lane, qa, qb, rg * 24);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[stage]);
