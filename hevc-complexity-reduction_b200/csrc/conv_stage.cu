@@ -18,18 +18,21 @@
 //       conv3  rows = quads (set A rows 0-7, set B rows 8-15), K = 96 = (region, channel): the conv2 C fragments
 //              of the four regions, in natural order, ARE the A fragments.
 //     Weights sit in shared memory pre-arranged as B fragments (one conflict-free 64-bit load per lane).
-//   * precision: every operand is split into fp16 hi + lo (after exact power-of-two scaling) and three MMAs
-//     (hi*hi, hi*lo, lo*hi) accumulate in fp32 -- 2^-22 relative, like the FC stages.  The mean removal is
-//     exact: with s = pooled integer sum and W = integer window sum, (256 s - W) / 32 is split exactly.
+//   * precision: conv1's A operand is the centred integer pooled sum s - 128 pool^2 (|.| <= 2048: exact in fp16), its
+//     filters are fp16 hi + lo (two MMAs); the mean removal is a per-window constant and moves into the bias:
+//     conv(s - mean) = conv(s - centre) + (centre - mean) * sum(taps).  Conv2 / conv3 operands are split into fp16
+//     hi + lo (after exact power-of-two scaling) and three MMAs (hi*hi, hi*lo, lo*hi) accumulate in fp32: 2^-22
+//     relative, like the FC stages.
 // A warp task is one CTU (S), four CTUs (M) or sixteen CTUs (L); a group of 16 CTUs is 16 + 4 + 1 = 21
-// warp tasks of identical MMA count (312 mma.sync each).  Round-1 history: an FFMA version of this stage
+// warp tasks of identical MMA count (280 mma.sync each).  Round-1 history: an FFMA version of this stage
 // reached 39 % of the fp32 peak and was bound by shared-memory wavefronts for the broadcast weights
 // (profiles/r01c_conv_v2.md); mma.sync does the same MACs 7.4x faster per SM (tools/microbench/hmma_rate.cu).
 //
 // A persistent CTA (one per SM) keeps the 58 KB of weight fragments resident in shared memory and streams
 // 16-CTU tile groups through a 2-deep TMA ring (3-D tensor map over (x, y, frame), 64x64x1 box; the zero
 // fill of out-of-bounds rows/columns IS the reference's zero padding, video_to_cu_depth.py:54-57).
-// One producer warp issues TMA, eleven compute warps take warp tasks round-robin.
+// One producer warp issues TMA and tabulates the 16x16-pixel block sums of the group (the mean-removal windows of
+// the three branches are 1, 4 and 16 of those blocks); eleven compute warps take warp tasks round-robin.
 #include <cstring>
 
 #include "kernels.h"
@@ -464,7 +467,7 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
       qb.hi = p.feat_hi + row_b, qb.lo = p.feat_lo + row_b;
       qa.c2_off = c2_base + ((2 * qy_a) * rg + 2 * qx) * 24, qb.c2_off = c2_base + ((2 * qy_b) * rg + 2 * qx) * 24;
       qa.c3_off = c3_base + (qy_a * qg + qx) * 32, qb.c3_off = c3_base + (qy_b * qg + qx) * 32;
-#ifdef ETHCNN_EXPERIMENT_S_ONLY
+#ifdef ETHCNN_EXPERIMENT_S_ONLY   // measurement only (wrong results): time the S tasks / the M and L tasks alone
       if (task < 16)
 #endif
 #ifdef ETHCNN_EXPERIMENT_ML_ONLY
