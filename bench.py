@@ -42,6 +42,10 @@ ALG_FLOP_PER_CTU = 3104298              # 2 * 1 552 149 MAC
 FC1_FLOP_PER_CTU = 2 * 1204224
 CONV_FLOP_PER_CTU = 2 * 279552
 FP32_FFMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal, not measured
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch over 25 500 CTUs, from the `ncu --set full` captures
+# summarised in profiles/r01f_conv_v4.md (conv) and profiles/r01e_fc_pair.md (fused FC), per CTU
+NCU_DRAM_BYTES_PER_CTU = {"conv": (104.528640e6 + 224.208384e6) / 25500, "fc1": (289.939456e6 + 5.607680e6) / 25500}
+NCU_DRAM_SOURCE = {"conv": "profiles/r01f_conv_v4.md", "fc1": "profiles/r01e_fc_pair.md"}
 
 
 def make_clip(seed0: int, n_base: int = 5) -> np.ndarray:
@@ -235,6 +239,16 @@ def run_ours(args):
     out_host = torch.empty((n_ctus, 21), dtype=torch.float32).pin_memory()
     gather_buf = [torch.empty_like(out_dev) for _ in range(world)] if (world > 1 and rank == 0) else None
     stream = torch.cuda.current_stream()
+    # N > 1: the per-rank rows reach rank 0 through a gather buffer in PEER memory (the gate kernel's stores cross
+    # NVLink; no collective on the data path).  If the devices cannot map each other: NCCL gather after the kernels.
+    peer = None
+    if world > 1 and not args.nccl_gather:
+        peer = eb.sharding.PeerGather(net, world * n_ctus, 21, dst=0, device=dev)
+        if not peer.ok:
+            if rank == 0:
+                print("[bench] peer gather buffer unavailable (%s): NCCL gather instead" % peer.error, file=sys.stderr)
+            peer = None
+    peer_out = peer.row_ptr(rank * n_ctus) if peer is not None else 0
 
     def barrier():
         if world > 1:
@@ -243,6 +257,9 @@ def run_ours(args):
 
     def step_device(i):
         k = i % 4
+        if peer is not None:   # rows land in rank 0's buffer as the kernels store them
+            net.predict_luma_device(clips_dev[k].data_ptr(), W, H, W, W * H, FRAMES, QPS[k], peer_out, stream.cuda_stream)
+            return
         net.predict_luma_device(clips_dev[k].data_ptr(), W, H, W, W * H, FRAMES, QPS[k], out_dev.data_ptr(), stream.cuda_stream)
         if world > 1:
             dist.gather(out_dev, gather_buf, dst=0)
@@ -286,6 +303,8 @@ def run_ours(args):
         return float(t.item())
 
     # ---- device-resident (kernel) number, with per-stage events
+    if peer is not None:
+        net.set_option(eb.OPT_STAGED_OUTPUT, 1)
     net.profile_enable(True)
     for s in range(4):
         net.profile_read(s, reset=True)
@@ -308,6 +327,20 @@ def run_ours(args):
     net.profile_enable(False)
     dev_ms = max_over_ranks(dev_ms)
     value = world * args.steps * n_ctus / (dev_ms * 1e-3)
+    gather_check = None
+    if peer is not None:
+        # outside the timed regions: the rows in rank 0's peer buffer must equal an NCCL gather of the same step
+        step_device(0)
+        peer.complete()
+        net.set_option(eb.OPT_STAGED_OUTPUT, 0)
+        net.predict_luma_device(clips_dev[0].data_ptr(), W, H, W, W * H, FRAMES, QPS[0], out_dev.data_ptr(), stream.cuda_stream)
+        dist.gather(out_dev, gather_buf, dst=0)
+        torch.cuda.synchronize()
+        if rank == 0:
+            same = bool(torch.equal(peer.rows(), torch.cat(gather_buf)))
+            gather_check = "rows in the peer buffer are bit-identical to an NCCL gather" if same else "MISMATCH against the NCCL gather"
+            if not same:
+                raise SystemExit("peer gather buffer differs from the NCCL gather")
 
     # ---- end to end through the host API (pinned host buffers; H2D + kernels + D2H inside the timed region)
     # the device timeline cannot see host work, so e2e is wall clock between synchronised barriers, max over ranks
@@ -337,9 +370,14 @@ def run_ours(args):
         # per-kernel algorithmic work: CONV 559 104 FLOP/CTU, dense stages 2 545 194 FLOP/CTU
         kern = {"conv": (CONV_FLOP_PER_CTU, conv_s), "fc1": (ALG_FLOP_PER_CTU - CONV_FLOP_PER_CTU, fc_s)}
         dom = "conv" if conv_s >= fc_s else "fc1"
+        kfeat = 2688   # features per CTU; the kernels exchange them as fp16 hi + lo (2 x 2 x 2688 B per CTU)
         flop, secs = kern[dom]
         roofline = {"kernel": dom if dom == "conv" else "fc (FC1+FC2+FC3)", "bound": "tensor",
-                    "achieved": ctus_timed * flop / secs / 1e12, "peak": tf_peak, "unit": "TFLOP/s", "traffic": None,
+                    "achieved": ctus_timed * flop / secs / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
+                    "traffic": NCU_DRAM_BYTES_PER_CTU[dom] * ctus_timed / max(1, stage[dom]["launches"]),
+                    "traffic_source": "dram bytes read + written per launch, scaled per CTU from " + NCU_DRAM_SOURCE[dom],
+                    "algorithmic_bytes_per_launch": (4096 + 2 * 2 * kfeat if dom == "conv" else 2 * 2 * kfeat + 84)
+                                                    * ctus_timed / max(1, stage[dom]["launches"]),
                     "peak_source": peak_src + ", sustained bf16",
                     "avg_launch_ms": stage[dom]["ms_total"] / max(1, stage[dom]["launches"]),
                     "note": "algorithmic FLOPs of the kernel / its CUDA-event time; the kernel issues 3x these FLOPs in fp16 "
@@ -378,7 +416,12 @@ def run_ours(args):
             "data": "synthetic luma; weights: %s" % ("deployed checkpoints" if not synthetic else
                                                      "synthetic checkpoints for QP %s" % synthetic),
             "config": {"workload": "config2: 1920x1080 4:2:0, 50 frames per rank per step, QP cycling 22/27/32/37",
-                       "ctus_per_step": world * n_ctus, "sharding": "contiguous frame ranges, NCCL gather to rank 0" if world > 1 else "single GPU",
+                       "ctus_per_step": world * n_ctus,
+                       "sharding": ("single GPU" if world == 1 else
+                                    "contiguous frame ranges; rows stored by the gate kernel straight into rank 0's gather buffer over "
+                                    "NVLink peer memory (no collective on the data path); e2e: NCCL gather" if peer is not None else
+                                    "contiguous frame ranges, NCCL gather to rank 0"),
+                       "gather_check": gather_check,
                        "l2": "inputs rotate over 4 clips (415 MB luma) + ~600 MB of scratch traffic per step, larger than the 126 MB L2",
                        "dense_path": ("simt", "tcgen05 FC1 + heads kernel", "fused tcgen05 FC1+FC2+FC3",
                                       "fused tcgen05 FC1+FC2+FC3 on CTA pairs (cta_group::2)")[net.query(3)]},
@@ -395,6 +438,8 @@ def run_ours(args):
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line))
+    if peer is not None:
+        peer.close()
     net.close()
     if world > 1:
         dist.barrier()
@@ -409,6 +454,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-gather", action="store_true", help="N > 1: gather with NCCL after the kernels instead of peer-memory stores")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     if args.impl == "reference":

@@ -21,6 +21,9 @@ from .binding import (  # noqa: F401
     STAGE_HEADS,
     STAGE_GATE,
     STAGE_NAMES,
+    OPT_FC1_PATH,
+    OPT_CHUNK_CTUS,
+    OPT_STAGED_OUTPUT,
     library_path,
     load_library,
     ctu_grid,

@@ -17,7 +17,8 @@ STAGE_CONV, STAGE_FC1, STAGE_HEADS, STAGE_GATE = 0, 1, 2, 3
 STAGE_NAMES = ("conv", "fc1", "heads", "gate")
 
 Q_KERNEL_LAUNCHES, Q_N_DEVICES, Q_FC1_PATH, Q_TMA_LOADER_USED, Q_SM_COUNT = 1, 2, 3, 4, 5
-OPT_FC1_PATH, OPT_CHUNK_CTUS = 1, 2
+OPT_FC1_PATH, OPT_CHUNK_CTUS, OPT_STAGED_OUTPUT = 1, 2, 3
+IPC_HANDLE_BYTES = 64
 
 _LIB = None
 
@@ -60,6 +61,9 @@ def load_library() -> C.CDLL:
         "ethcnn_profile_enable": (i32, [vp, i32]),
         "ethcnn_profile_read": (i32, [vp, i32, C.POINTER(C.c_double), C.POINTER(i64), i32]),
         "ethcnn_set_option": (i32, [vp, i32, i64]),
+        "ethcnn_peer_buffer_create": (i32, [vp, sz, C.POINTER(vp), vp]),
+        "ethcnn_peer_buffer_open": (i32, [vp, vp, C.POINTER(vp)]),
+        "ethcnn_peer_buffer_release": (i32, [vp, vp]),
         "ethcnn_alloc_pinned": (vp, [sz]),
         "ethcnn_free_pinned": (None, [vp]),
         "ethcnn_debug_pack_model": (i32, [cp, C.c_float, vp, vp, vp, vp, vp, vp, vp]),
@@ -230,6 +234,26 @@ class EthCnn(object):
 
     def set_option(self, option: int, value: int) -> None:
         _check(self._lib.ethcnn_set_option(self._h, option, value))
+
+    # --- gather buffers in peer memory (include/ethcnn.h: "Multi-GPU gather without a collective")
+    def peer_buffer_create(self, n_bytes: int) -> Tuple[int, bytes]:
+        """(device pointer, 64-byte IPC handle) of a zero-filled buffer on this handle's device."""
+        p = C.c_void_p()
+        hb = (C.c_uint8 * IPC_HANDLE_BYTES)()
+        _check(self._lib.ethcnn_peer_buffer_create(self._h, n_bytes, C.byref(p), C.cast(hb, C.c_void_p)))
+        return int(p.value), bytes(hb)
+
+    def peer_buffer_open(self, handle: bytes) -> int:
+        """Map a buffer another process exported; raises EthCnnError when the devices cannot reach each other."""
+        if len(handle) != IPC_HANDLE_BYTES:
+            raise EthCnnError(-1, "an IPC handle has %d bytes" % IPC_HANDLE_BYTES)
+        p = C.c_void_p()
+        hb = (C.c_uint8 * IPC_HANDLE_BYTES).from_buffer_copy(handle)
+        _check(self._lib.ethcnn_peer_buffer_open(self._h, C.cast(hb, C.c_void_p), C.byref(p)))
+        return int(p.value)
+
+    def peer_buffer_release(self, d_ptr: int) -> None:
+        _check(self._lib.ethcnn_peer_buffer_release(self._h, C.c_void_p(d_ptr)))
 
     def profile_enable(self, on: bool = True) -> None:
         _check(self._lib.ethcnn_profile_enable(self._h, 1 if on else 0))

@@ -189,6 +189,30 @@ __global__ void gate_kernel(float* __restrict__ prob, const unsigned* __restrict
   if (!keep) prob[n * kProbs + slot] = 0.0f;
 }
 
+// GATE + EXPORT: the same rule, reading the raw probabilities from a library-owned staging buffer and writing the final
+// rows to `dst` with consecutive threads on consecutive floats (full 128-byte store transactions per warp).  Used when
+// dst is PEER memory (another GPU's gather buffer mapped over NVLink, ethcnn_peer_buffer_open): the dense kernel's own
+// 4-byte row-strided stores would cross the link as one small packet each.  flags == nullptr: no gates (LDP CNN).
+__global__ void gate_export_kernel(const float* __restrict__ src, float* __restrict__ dst, const unsigned* __restrict__ flags,
+                                   float t2, long long n_total, int ctus_per_frame, int chunks_per_frame) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // one thread per float
+  if (i >= n_total * kProbs) return;
+  float v = src[i];
+  if (flags != nullptr) {
+    const long long n = i / kProbs;
+    const int slot = int(i - n * kProbs);
+    if (slot > 0) {
+      const long long f = n / ctus_per_frame;
+      const int r = int(n - f * ctus_per_frame);
+      const unsigned fl = flags[f * chunks_per_frame + r / kSubBatch];
+      const bool g1 = (fl & 1u) != 0;
+      const bool g2 = g1 ? ((fl & 2u) != 0) : (0.0f > t2);
+      if (!((slot < 5) ? g1 : g2)) v = 0.0f;
+    }
+  }
+  dst[i] = v;
+}
+
 __global__ void decisions_kernel(const float* __restrict__ prob, unsigned char* __restrict__ dec, long long n_values,
                                  const float* __restrict__ thr6) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -228,6 +252,14 @@ cudaError_t launch_gate(float* prob, const unsigned* flags, float t2, long long 
   if (n_total <= 0) return cudaSuccess;
   const long long work = n_total * 20;
   gate_kernel<<<unsigned((work + 255) / 256), 256, 0, stream>>>(prob, flags, t2, n_total, ctus_per_frame, chunks_per_frame);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gate_export(const float* src, float* dst, const unsigned* flags, float t2, long long n_total,
+                               int ctus_per_frame, int chunks_per_frame, cudaStream_t stream) {
+  if (n_total <= 0) return cudaSuccess;
+  const long long work = n_total * kProbs;
+  gate_export_kernel<<<unsigned((work + 255) / 256), 256, 0, stream>>>(src, dst, flags, t2, n_total, ctus_per_frame, chunks_per_frame);
   return cudaGetLastError();
 }
 

@@ -96,6 +96,10 @@ struct DeviceCtx {
   float* fc1 = nullptr;
   unsigned* flags = nullptr;
   size_t flags_cap = 0;
+  float* gprob = nullptr;         // staged raw probabilities (ETHCNN_OPT_STAGED_OUTPUT): the gate kernel exports them
+  size_t gprob_floats = 0;
+  std::vector<void*> peer_owned;  // gather buffers this device exported (ethcnn_peer_buffer_create)
+  std::vector<void*> peer_opened; // peer buffers mapped into this process (ethcnn_peer_buffer_open)
   cudaEvent_t ev_last = nullptr;  // end of the previous device call (scratch reuse across streams)
   // staging for the host path
   static constexpr int kSlabs = 3;
@@ -140,6 +144,7 @@ struct ethcnn_handle {
   // 3 = the fused kernel on CTA pairs (cta_group::2)
   int fc1_path = 3;
   size_t chunk_ctus = 148 * 256;   // 74 CTA pairs x 2 column tiles x 256 CTUs: four fused-FC tiles per pair, 16 conv groups per CTA
+  bool staged_output = false;      // device path: dense kernel -> local staging -> gate kernel exports with coalesced stores
 };
 
 namespace ethcnn {
@@ -376,6 +381,19 @@ int run_device(ethcnn_handle* h, DeviceCtx& c, const uint8_t* d_y, int width, in
   const bool use_tma = make_luma_tensor_map(&tmap, d_y, width, height, n_frames, pitch, frame_stride, &terr);
   c.last_used_tma = use_tma ? 1 : 0;
   const bool gated = ((h->mode == ETHCNN_MODE_AI) && fc1_out == nullptr) || ldp != nullptr;
+  // staged output: the dense kernels write their row-strided 4-byte stores to a local buffer and the gate kernel
+  // copies the finished rows to d_out (peer memory over NVLink in the multi-GPU gather) with coalesced stores
+  const bool staged = h->staged_output && fc1_out == nullptr && ldp == nullptr && d_out != nullptr;
+  float* const final_out = d_out;
+  if (staged) {
+    if (size_t(total) * kProbs > c.gprob_floats) {
+      cudaFree(c.gprob);
+      c.gprob = nullptr, c.gprob_floats = 0;
+      CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c.gprob), size_t(total) * kProbs * 4));
+      c.gprob_floats = size_t(total) * kProbs;
+    }
+    d_out = c.gprob;
+  }
   if (gated) CUDA_TRY(cudaMemsetAsync(c.flags, 0, size_t(n_frames) * chunks_per_frame * sizeof(unsigned), stream));
 
   const float in_scale = (h->mode == ETHCNN_MODE_LDP) ? (10.0f / 255.0f) : (1.0f / 255.0f);
@@ -469,7 +487,11 @@ int run_device(ethcnn_handle* h, DeviceCtx& c, const uint8_t* d_y, int width, in
       ++h->launches;
     }
   }
-  if (gated) {
+  if (staged) {
+    StageTimer t(c, stream, ETHCNN_STAGE_GATE);
+    CUDA_TRY(launch_gate_export(d_out, final_out, gated ? c.flags : nullptr, h->t2, total, ctus_per_frame, chunks_per_frame, stream));
+    ++h->launches;
+  } else if (gated) {
     StageTimer t(c, stream, ETHCNN_STAGE_GATE);
     CUDA_TRY(launch_gate(d_out, c.flags, h->t2, total, ctus_per_frame, chunks_per_frame, stream));
     ++h->launches;
@@ -599,7 +621,9 @@ int run_host_pipeline(ethcnn_handle* h, DeviceCtx& c, const uint8_t* y, int widt
       src = c.h_stage[b];
       src_stride = luma_bytes;
     }
-    if (pitch == size_t(width)) {
+    if (pitch == size_t(width) && src_stride == luma_bytes) {   // luma-only clip: one contiguous copy
+      CUDA_TRY(cudaMemcpyAsync(c.d_slab[b], src, luma_bytes * nf, cudaMemcpyHostToDevice, c.s_h2d));
+    } else if (pitch == size_t(width)) {
       CUDA_TRY(cudaMemcpy2DAsync(c.d_slab[b], dev_frame, src, src_stride, luma_bytes, nf, cudaMemcpyHostToDevice, c.s_h2d));
     } else {
       for (int f = 0; f < nf; ++f)
@@ -839,7 +863,9 @@ void close_device(DeviceCtx& c) {
   for (auto& kv : c.models) free_model(kv.second);
   for (auto& kv : c.lstm_models) cudaFree(kv.second.blob);
   cudaFree(c.d_state_in), cudaFree(c.d_state_out), cudaFree(c.d_z), cudaFree(c.d_beff), cudaFreeHost(c.h_beff);
-  cudaFree(c.feat_hi), cudaFree(c.feat_lo), cudaFree(c.fc1), cudaFree(c.flags);
+  cudaFree(c.feat_hi), cudaFree(c.feat_lo), cudaFree(c.fc1), cudaFree(c.flags), cudaFree(c.gprob);
+  for (void* p : c.peer_opened) cudaIpcCloseMemHandle(p);
+  for (void* p : c.peer_owned) cudaFree(p);
   for (int i = 0; i < DeviceCtx::kSlabs; ++i) {
     cudaFree(c.d_slab[i]), cudaFree(c.d_prob[i]), cudaFreeHost(c.h_stage[i]), cudaFreeHost(c.h_prob[i]);
     if (c.ev_h2d[i]) cudaEventDestroy(c.ev_h2d[i]);
@@ -1107,9 +1133,74 @@ int ethcnn_set_option(ethcnn_handle* h, int option, int64_t value) {
       if (value < 1 || value > (1 << 22)) return fail(ETHCNN_E_ARG, "chunk size out of range");
       h->chunk_ctus = size_t(value);
       break;
+    case ETHCNN_OPT_STAGED_OUTPUT:
+      h->staged_output = value != 0;
+      break;
     default: return fail(ETHCNN_E_ARG, "unknown option");
   }
   return ETHCNN_OK;
+}
+
+// ---- gather buffers in peer memory (one process per GPU; the rows travel over NVLink as the kernels store them)
+int ethcnn_peer_buffer_create(ethcnn_handle* h, size_t bytes, void** d_ptr, uint8_t handle_out[ETHCNN_IPC_HANDLE_BYTES]) {
+  if (!h || !d_ptr || !handle_out || bytes == 0) return fail(ETHCNN_E_ARG, "NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == ETHCNN_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceCtx& c = *h->devs[0];
+  CUDA_TRY(cudaSetDevice(c.device));
+  void* p = nullptr;
+  CUDA_TRY(cudaMalloc(&p, bytes));   // its own allocation: an IPC handle always names a whole cudaMalloc block
+  cudaIpcMemHandle_t mh;
+  cudaError_t e = cudaMemset(p, 0, bytes);
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&mh, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return fail(ETHCNN_E_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+  }
+  memcpy(handle_out, &mh, sizeof(mh));
+  c.peer_owned.push_back(p);
+  *d_ptr = p;
+  return ETHCNN_OK;
+}
+
+int ethcnn_peer_buffer_open(ethcnn_handle* h, const uint8_t handle[ETHCNN_IPC_HANDLE_BYTES], void** d_ptr) {
+  if (!h || !d_ptr || !handle) return fail(ETHCNN_E_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceCtx& c = *h->devs[0];
+  CUDA_TRY(cudaSetDevice(c.device));
+  cudaIpcMemHandle_t mh;
+  memcpy(&mh, handle, sizeof(mh));
+  void* p = nullptr;
+  // maps the exporter's allocation into this process and enables peer access between the two devices
+  cudaError_t e = cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ETHCNN_E_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+  }
+  c.peer_opened.push_back(p);
+  *d_ptr = p;
+  return ETHCNN_OK;
+}
+
+int ethcnn_peer_buffer_release(ethcnn_handle* h, void* d_ptr) {
+  if (!h || !d_ptr) return fail(ETHCNN_E_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceCtx& c = *h->devs[0];
+  CUDA_TRY(cudaSetDevice(c.device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  for (size_t i = 0; i < c.peer_opened.size(); ++i)
+    if (c.peer_opened[i] == d_ptr) {
+      c.peer_opened.erase(c.peer_opened.begin() + i);
+      CUDA_TRY(cudaIpcCloseMemHandle(d_ptr));
+      return ETHCNN_OK;
+    }
+  for (size_t i = 0; i < c.peer_owned.size(); ++i)
+    if (c.peer_owned[i] == d_ptr) {
+      c.peer_owned.erase(c.peer_owned.begin() + i);
+      CUDA_TRY(cudaFree(d_ptr));
+      return ETHCNN_OK;
+    }
+  return fail(ETHCNN_E_ARG, "not a peer buffer of this handle");
 }
 
 int ethcnn_profile_enable(ethcnn_handle* h, int on) {

@@ -104,6 +104,11 @@ cudaError_t launch_heads(const HeadsLaunch& p, cudaStream_t stream);
 cudaError_t launch_gate(float* prob, const unsigned* flags, float t2, long long n_total, int ctus_per_frame,
                         int chunks_per_frame, cudaStream_t stream);
 
+// Gates applied while copying the raw probabilities from a staging buffer to their destination with coalesced stores
+// (the destination may be peer memory over NVLink); flags == nullptr copies without gates.
+cudaError_t launch_gate_export(const float* src, float* dst, const unsigned* flags, float t2, long long n_total,
+                               int ctus_per_frame, int chunks_per_frame, cudaStream_t stream);
+
 // One LSTM step for the three heads (lstm_stage.cu).  state rows are [c(448) | h(448)]; z_scratch is [rows][1792].
 cudaError_t launch_lstm_step(const float* fc1, const float* state_in, float* state_out, float* z_scratch,
                              const float* const kernel[3], const float* const bias[3], int rows, cudaStream_t stream);

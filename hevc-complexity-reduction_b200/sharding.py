@@ -3,8 +3,14 @@
 The path shards on independent units: every frame is independent and the per-sub-batch gates never
 cross a frame (video_to_cu_depth.py:64-70, net_CNN.py:175,187), so rank r takes a contiguous frame
 range and the only exchange is the gather of the per-rank cu_depth rows to rank 0, which serialises
-them (video_to_cu_depth.py:114-116).  Over NCCL this is a grouped send/recv (torch.distributed.gather);
-the same code runs over gloo on CPU tensors in the tests.
+them (video_to_cu_depth.py:114-116).  Two transports:
+
+* ``gather_rows``  -- a collective after the kernels: grouped send/recv (torch.distributed.gather) over NCCL, or
+  over gloo on CPU tensors in the tests;
+* ``PeerGather``   -- no collective on the data path: rank dst exports ONE buffer for the whole sequence
+  (include/ethcnn.h, ethcnn_peer_buffer_*), every rank maps it over NVLink / NVSwitch and hands
+  ``buffer + first_row_of_rank * 84`` to the kernels as their output pointer, so the gate kernel's coalesced
+  stores are the transfer.  torch.distributed only carries the 64-byte handle and the closing barrier.
 """
 from __future__ import annotations
 
@@ -43,6 +49,106 @@ def gather_rows(local_rows, n_frames: int, rows_per_frame: int, row_width: int, 
     if rank != dst:
         return None
     return torch.cat([recv[r][: ranges[r][1] * rows_per_frame] for r in range(world)], dim=0)
+
+
+class _DevicePointerView(object):
+    """__cuda_array_interface__ wrapper so torch can view a raw device pointer without copying."""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+class PeerGather(object):
+    """The gather buffer of one sharded prediction, living on rank `dst` and written in place by every rank.
+
+    `net` is this rank's EthCnn (or anything with peer_buffer_create / peer_buffer_open / peer_buffer_release).
+    After construction `ok` says whether EVERY rank could map the buffer (agreed with a MIN all-reduce); if not,
+    nothing stays mapped and the caller uses gather_rows().  Usage on every rank:
+
+        pg = PeerGather(net, total_rows)
+        net.set_option(OPT_STAGED_OUTPUT, 1)
+        net.predict_luma_device(..., d_out=pg.row_ptr(first_row_of_this_rank), stream=...)
+        pg.complete()                       # stream sync + barrier: all rows are now in rank dst's memory
+        rows = pg.rows()                    # rank dst: zero-copy torch view [total_rows, row_width]; None elsewhere
+    """
+
+    def __init__(self, net, total_rows: int, row_width: int = 21, dst: int = 0, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+
+        self.net, self.total_rows, self.row_width, self.dst, self.group = net, int(total_rows), int(row_width), dst, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = device
+        self.ptr = 0
+        self.error = None
+        n_bytes = max(4, self.total_rows * self.row_width * 4)
+        box = [None]
+        if self.rank == dst:
+            try:
+                self.ptr, box[0] = net.peer_buffer_create(n_bytes)
+            except Exception as e:  # no device / allocation failure: every rank learns about it below
+                self.error = str(e)
+        dist.broadcast_object_list(box, src=dst, group=group)
+        mine = 1
+        if self.rank != dst:
+            if box[0] is None:
+                mine = 0
+            else:
+                try:
+                    self.ptr = net.peer_buffer_open(box[0])
+                except Exception as e:
+                    self.error, mine = str(e), 0
+        elif box[0] is None:
+            mine = 0
+        flag = torch.tensor([mine], dtype=torch.int32, device=device if device is not None else "cpu")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        self.ok = bool(int(flag.item()) == 1)
+        if not self.ok:
+            self.close()
+
+    def row_ptr(self, first_row: int) -> int:
+        """Address of row `first_row` (frame-major CTU raster order) inside the gather buffer."""
+        if not self.ok:
+            raise RuntimeError("peer gather buffer is not mapped on every rank: %s" % (self.error or "a peer failed"))
+        if not 0 <= first_row <= self.total_rows:
+            raise ValueError("row outside the gather buffer")
+        return self.ptr + int(first_row) * self.row_width * 4
+
+    def complete(self) -> None:
+        """Every rank's stores have landed on rank dst: local device sync, then a barrier."""
+        import torch
+        import torch.distributed as dist
+
+        if self.device is not None and torch.cuda.is_available():
+            torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+
+    def rows(self):
+        """Rank dst: the gathered [total_rows, row_width] float32 rows as a zero-copy torch tensor on its device."""
+        import torch
+
+        if self.rank != self.dst or not self.ok:
+            return None
+        return torch.as_tensor(_DevicePointerView(self.ptr, (self.total_rows, self.row_width)), device=self.device)
+
+    def close(self) -> None:
+        """Collective: every rank calls it.  Importers unmap first, the exporter frees after a barrier."""
+        import torch.distributed as dist
+
+        def release():
+            if self.ptr:
+                try:
+                    self.net.peer_buffer_release(self.ptr)
+                except Exception:
+                    pass
+                self.ptr = 0
+
+        if self.rank != self.dst:
+            release()
+        dist.barrier(group=self.group)
+        if self.rank == self.dst:
+            release()
+        self.ok = False
 
 
 def predict_sharded(predict_frames: Callable[[int, int], "object"], n_frames: int, rows_per_frame: int,

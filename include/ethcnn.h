@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define ETHCNN_ABI_VERSION 1
+#define ETHCNN_ABI_VERSION 2 /* 2: staged output option + peer gather buffers */
 
 /* Which network/deployment is evaluated. */
 #define ETHCNN_MODE_AI  0 /* HM-16.5_Test_AI/bin/net_CNN.py:103-195 (x/255, qp/51, batch-level gates)      */
@@ -151,7 +151,30 @@ int ethcnn_profile_read(ethcnn_handle* h, int stage, double* ms_total, int64_t* 
                                     2 = fused tcgen05 FC1+FC2+FC3, one CTA per 128 CTUs,
                                     3 = the fused kernel on CTA pairs (tcgen05 cta_group::2, 256 CTUs per pair) */
 #define ETHCNN_OPT_CHUNK_CTUS  2 /* CTUs per feature-buffer chunk                    */
+#define ETHCNN_OPT_STAGED_OUTPUT 3 /* ethcnn_predict_luma_device only. 1 = the dense kernel writes its raw probabilities to a
+                                    library-owned local buffer and the gate kernel copies the finished rows to d_out with
+                                    coalesced stores: set it when d_out is PEER memory (ethcnn_peer_buffer_open), so that the
+                                    rows cross NVLink as full 128-byte transactions.  0 (default) = rows are written in place */
 int ethcnn_set_option(ethcnn_handle* h, int option, int64_t value);
+
+/*
+ * Multi-GPU gather without a collective (one process per GPU).  The reference serialises all
+ * probabilities in one process (video_to_cu_depth.py:114-116); when frames are sharded over ranks the per-rank rows have
+ * to reach rank 0.  Instead of a gather AFTER the kernels, rank 0 exports one buffer for the whole sequence, every other
+ * rank maps it (CUDA IPC; peer access over NVLink / NVSwitch is enabled by the mapping) and passes
+ * `peer + first_row_of_rank * 21` as d_out of ethcnn_predict_luma_device with ETHCNN_OPT_STAGED_OUTPUT = 1: the gate
+ * kernel's stores ARE the transfer.  The rows are complete on rank 0 once every rank has synchronised its stream and
+ * the ranks have met at a barrier.  The 64-byte handle travels through whatever the ranks share (torch.distributed
+ * broadcast in sharding.py).
+ *   ethcnn_peer_buffer_create   cudaMalloc on the handle's device + export; the buffer is zero-filled
+ *   ethcnn_peer_buffer_open     map another process's buffer; fails with ETHCNN_E_CUDA when the devices cannot reach each
+ *                               other (the caller then falls back to an NCCL gather)
+ *   ethcnn_peer_buffer_release  unmap (opened) or free (created); ethcnn_destroy releases what is left
+ */
+#define ETHCNN_IPC_HANDLE_BYTES 64
+int ethcnn_peer_buffer_create(ethcnn_handle* h, size_t bytes, void** d_ptr, uint8_t handle_out[ETHCNN_IPC_HANDLE_BYTES]);
+int ethcnn_peer_buffer_open(ethcnn_handle* h, const uint8_t handle[ETHCNN_IPC_HANDLE_BYTES], void** d_ptr);
+int ethcnn_peer_buffer_release(ethcnn_handle* h, void* d_ptr);
 
 /* Pinned host memory helpers (so foreign-language callers can hand over page-locked buffers). */
 void* ethcnn_alloc_pinned(size_t bytes);
