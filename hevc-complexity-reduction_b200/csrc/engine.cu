@@ -272,6 +272,8 @@ int get_model(ethcnn_handle* h, DeviceCtx& c, int qp, DeviceModel** out) {
   m.w2_exp = pm.w2_exp;
   if (!fc_fused_prepare_weights(m.w1_hi, m.w1_lo, m.w2_hi, m.w2_lo, &m.fused, &terr))
     return fail(ETHCNN_E_CUDA, std::string("fused FC weight tensor maps: ") + terr);
+  // cudaMemcpy from pageable memory may return before the DMA has landed, and the kernels run on non-blocking streams
+  CUDA_TRY(cudaDeviceSynchronize());
   auto ins = c.models.emplace(prefix, m);
   *out = &ins.first->second;
   return ETHCNN_OK;
@@ -290,6 +292,9 @@ int ensure_scratch(ethcnn_handle* h, DeviceCtx& c, size_t flags_needed) {
     CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c.fc1), rows * kFc1 * 4));
     CUDA_TRY(cudaMemset(c.feat_hi, 0, rows * kFeat * 2));
     CUDA_TRY(cudaMemset(c.feat_lo, 0, rows * kFeat * 2));
+    // The fills run on the legacy stream, which does NOT order against the non-blocking streams the kernels use:
+    // without this the zero fill of a fresh handle's buffers could land on top of the first slab's features.
+    CUDA_TRY(cudaDeviceSynchronize());
   }
   if (flags_needed > c.flags_cap) {
     cudaFree(c.flags);
@@ -741,6 +746,7 @@ int get_lstm_model(ethcnn_handle* h, DeviceCtx& c, int qp, LstmDeviceModel** out
     m.kernel[k] = m.blob + off_k[k], m.bias[k] = m.blob + off_b[k];
     m.hw[k].w2 = m.blob + off_w2[k], m.hw[k].w3 = m.blob + off_w3[k];
   }
+  CUDA_TRY(cudaDeviceSynchronize());   // as in get_model: the upload must have landed before non-blocking streams use it
   auto ins = c.lstm_models.emplace(prefix, std::move(m));
   *out = &ins.first->second;
   return ETHCNN_OK;
@@ -1152,6 +1158,7 @@ int ethcnn_peer_buffer_create(ethcnn_handle* h, size_t bytes, void** d_ptr, uint
   CUDA_TRY(cudaMalloc(&p, bytes));   // its own allocation: an IPC handle always names a whole cudaMalloc block
   cudaIpcMemHandle_t mh;
   cudaError_t e = cudaMemset(p, 0, bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = cudaIpcGetMemHandle(&mh, p);
   if (e != cudaSuccess) {
     cudaFree(p);

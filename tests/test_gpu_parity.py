@@ -257,6 +257,20 @@ def test_pinned_and_pageable_hosts_agree(eb, ai_model_dir):
         assert np.array_equal(out.numpy(), a)
 
 
+def test_first_call_on_a_fresh_handle_is_clean(eb, ai_model_dir):
+    """Regression: the one-off zero fill of the feature buffers and the weight upload happen inside the FIRST call of a
+    handle (what the CLI does every run) and used to race with that call's kernels on the non-blocking streams (the lo
+    halves of some feature rows were zeroed: |dp| up to 2e-4).  First and second call must agree bit for bit."""
+    d, _ = ai_model_dir
+    W, H, nf, qp = 1920, 1080, 7, 32
+    yuv = np.frombuffer(eo.synth_yuv(W, H, nf, seed0=2), np.uint8)
+    for _ in range(3):
+        with eb.EthCnn(d, None, eb.MODE_AI, n_gpus=1) as fresh:
+            first = fresh.predict_yuv_buffer(yuv, W, H, qp)
+            again = fresh.predict_yuv_buffer(yuv, W, H, qp)
+        assert np.array_equal(first, again)
+
+
 def test_in_library_multi_gpu_matches_single(eb, ai_model_dir):
     import torch
 
