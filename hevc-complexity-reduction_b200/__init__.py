@@ -24,6 +24,8 @@ from .binding import (  # noqa: F401
     OPT_FC1_PATH,
     OPT_CHUNK_CTUS,
     OPT_STAGED_OUTPUT,
+    OPT_CONV_PATH,
+    Q_CONV_PATH,
     library_path,
     load_library,
     ctu_grid,

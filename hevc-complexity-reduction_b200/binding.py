@@ -16,8 +16,8 @@ FC1_WIDTH = 448
 STAGE_CONV, STAGE_FC1, STAGE_HEADS, STAGE_GATE = 0, 1, 2, 3
 STAGE_NAMES = ("conv", "fc1", "heads", "gate")
 
-Q_KERNEL_LAUNCHES, Q_N_DEVICES, Q_FC1_PATH, Q_TMA_LOADER_USED, Q_SM_COUNT = 1, 2, 3, 4, 5
-OPT_FC1_PATH, OPT_CHUNK_CTUS, OPT_STAGED_OUTPUT = 1, 2, 3
+Q_KERNEL_LAUNCHES, Q_N_DEVICES, Q_FC1_PATH, Q_TMA_LOADER_USED, Q_SM_COUNT, Q_CONV_PATH = 1, 2, 3, 4, 5, 6
+OPT_FC1_PATH, OPT_CHUNK_CTUS, OPT_STAGED_OUTPUT, OPT_CONV_PATH = 1, 2, 3, 4
 IPC_HANDLE_BYTES = 64
 
 _LIB = None

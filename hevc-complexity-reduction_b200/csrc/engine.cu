@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "../../include/ethcnn.h"
+#include "conv_tc.h"
 #include "fc1_tc.h"
 #include "fc_fused.h"
 #include "kernels.h"
@@ -52,6 +53,8 @@ int fail(int code, const std::string& msg) {
 
 struct DeviceModel {
   float* conv = nullptr;
+  uint8_t* conv_tc = nullptr;  // the conv filters as swizzled UMMA tiles (conv_tc.h)
+  float conv_hdr[3][4] = {};   // per branch: 32 * 2^-e1w, 2^-(e_c1 + e2w), 2^-(feat_exp + e3w), 2^e_c1 (kernels.h kHdrOff)
   float* w1 = nullptr;
   float* b1 = nullptr;
   __half* w1_hi = nullptr;
@@ -144,6 +147,7 @@ struct ethcnn_handle {
   // 3 = the fused kernel on CTA pairs (cta_group::2)
   int fc1_path = 3;
   size_t chunk_ctus = 148 * 256;   // 74 CTA pairs x 2 column tiles x 256 CTUs: four fused-FC tiles per pair, 16 conv groups per CTA
+  int conv_path = 0;               // 0 = mma.sync conv kernel (conv_stage.cu), 1 = tcgen05 conv kernel (conv_tc.cu)
   bool staged_output = false;      // device path: dense kernel -> local staging -> gate kernel exports with coalesced stores
 };
 
@@ -209,7 +213,7 @@ int upload(T** dst, const void* src, size_t bytes) {
 }
 
 void free_model(DeviceModel& m) {
-  cudaFree(m.conv), cudaFree(m.w1), cudaFree(m.b1), cudaFree(m.w1_hi), cudaFree(m.w1_lo), cudaFree(m.heads);
+  cudaFree(m.conv), cudaFree(m.conv_tc), cudaFree(m.w1), cudaFree(m.b1), cudaFree(m.w1_hi), cudaFree(m.w1_lo), cudaFree(m.heads);
   for (int k = 0; k < 3; ++k) cudaFree(m.w2_hi[k]), cudaFree(m.w2_lo[k]);
   cudaFree(m.w3_packed);
   m = DeviceModel();
@@ -234,6 +238,9 @@ int get_model(ethcnn_handle* h, DeviceCtx& c, int qp, DeviceModel** out) {
   DeviceModel m;
   int rc;
   if ((rc = upload(&m.conv, pm.conv.data(), pm.conv.size() * 4))) return rc;
+  if ((rc = upload(&m.conv_tc, pm.conv_tc.data(), pm.conv_tc.size()))) return rc;
+  for (int br = 0; br < 3; ++br)
+    for (int i = 0; i < 4; ++i) m.conv_hdr[br][i] = pm.conv[size_t(br) * kConvBranchFloats + kHdrOff + i];
   if ((rc = upload(&m.w1, pm.w1.data(), pm.w1.size() * 4))) return rc;
   if ((rc = upload(&m.b1, pm.b1.data(), pm.b1.size() * 4))) return rc;
   if ((rc = upload(&m.w1_hi, pm.w1_hi.data(), pm.w1_hi.size() * 2))) return rc;
@@ -413,7 +420,24 @@ int run_device(ethcnn_handle* h, DeviceCtx& c, const uint8_t* d_y, int width, in
     cl.feat_scale = std::ldexp(1.0f, m->feat_exp);
     c.last_feat_exp = m->feat_exp;
     cl.luma = d_y, cl.pitch = pitch, cl.frame_stride = frame_stride, cl.width = width, cl.height = height;
-    {
+    if (h->conv_path == 1 && use_tma) {   // tensor-core conv stage; needs the TMA tile loader
+      ConvTcLaunch tl{};
+      tl.blob = m->conv_tc;
+      tl.feat_hi = c.feat_hi, tl.feat_lo = c.feat_lo;
+      tl.n_ctus = n, tl.ctu_begin = int(begin), tl.ctus_per_row = ctu_cols, tl.ctus_per_frame = ctus_per_frame;
+      for (int br = 0; br < 3; ++br) {
+        const float* hd = m->conv_hdr[br];
+        tl.u1[br] = hd[0] * cl.cst[br] * hd[3];
+        tl.u1x8[br] = 8.f * tl.u1[br];
+        tl.u2[br] = hd[1] * cl.feat_scale;
+        tl.u3[br] = hd[2] * cl.feat_scale;
+      }
+      tl.phase_mask = 7;
+      if (const char* e = getenv("ETHCNN_TC_PHASES")) tl.phase_mask = atoi(e);   // timing experiments (wrong results)
+      StageTimer t(c, stream, ETHCNN_STAGE_CONV);
+      CUDA_TRY(launch_conv_tc(tmap, tl, c.sm_count, stream));
+      ++h->launches;
+    } else {
       StageTimer t(c, stream, ETHCNN_STAGE_CONV);
       CUDA_TRY(launch_conv_features(use_tma ? &tmap : nullptr, cl, c.sm_count, stream));
       ++h->launches;
@@ -856,6 +880,7 @@ int open_device(ethcnn_handle* h, int device) {
   CUDA_TRY(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
   CUDA_TRY(conv_features_configure());
+  CUDA_TRY(conv_tc_configure());
   CUDA_TRY(fc1_tc_configure());
   CUDA_TRY(heads_configure());
   CUDA_TRY(fc_fused_configure());
@@ -897,6 +922,7 @@ int create_common(const char* model_dir, const char* thr_path, int mode, const s
     const long v = atol(e);
     if (v >= 1 && v <= (1 << 22)) h->chunk_ctus = size_t(v);
   }
+  if (const char* e = getenv("ETHCNN_CONV")) h->conv_path = (strcmp(e, "tc") == 0) ? 1 : 0;
   if (const char* e = getenv("ETHCNN_FC1")) h->fc1_path = (strcmp(e, "simt") == 0) ? 0 : (strcmp(e, "tc") == 0 ? 1 : (strcmp(e, "pair") == 0 ? 3 : 2));
   {
     const std::string tp = thr_path ? std::string(thr_path) : h->model_dir + "/Thr_info.txt";
@@ -1122,6 +1148,7 @@ int ethcnn_query(ethcnn_handle* h, int what, int64_t* value) {
     case ETHCNN_Q_FC1_PATH: *value = h->fc1_path; break;
     case ETHCNN_Q_TMA_LOADER_USED: *value = h->devs[0]->last_used_tma; break;
     case ETHCNN_Q_SM_COUNT: *value = h->devs[0]->sm_count; break;
+    case ETHCNN_Q_CONV_PATH: *value = h->conv_path; break;
     default: return fail(ETHCNN_E_ARG, "unknown query");
   }
   return ETHCNN_OK;
@@ -1138,6 +1165,10 @@ int ethcnn_set_option(ethcnn_handle* h, int option, int64_t value) {
     case ETHCNN_OPT_CHUNK_CTUS:
       if (value < 1 || value > (1 << 22)) return fail(ETHCNN_E_ARG, "chunk size out of range");
       h->chunk_ctus = size_t(value);
+      break;
+    case ETHCNN_OPT_CONV_PATH:
+      if (value < 0 || value > 1) return fail(ETHCNN_E_ARG, "conv path must be 0 or 1");
+      h->conv_path = int(value);
       break;
     case ETHCNN_OPT_STAGED_OUTPUT:
       h->staged_output = value != 0;

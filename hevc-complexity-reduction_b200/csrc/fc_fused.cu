@@ -68,36 +68,50 @@ template <int kCtas>
 __device__ __forceinline__ uint32_t idesc_f16(int n) {
   return (1u << 4) | (uint32_t(n >> 3) << 17) | (uint32_t((kBM * kCtas) >> 4) << 24);
 }
+// The MMA and commit wrappers are called by ALL lanes of the converged issuer warp with warp-uniform operands; elect.sync
+// picks the one lane that really issues.  (Issued from inside `if (lane == 0)`, ptxas wraps every tcgen05.mma in a divergence
+// "waterfall" loop -- ELECT / R2UR.BROADCAST / BRA.U.ANY -- that costs ~110 cycles per MMA (tools/microbench/umma_probe.cu),
+// about as much as the MMA itself.)
 template <int kCtas>
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   if (kCtas == 1)
     asm volatile(
         "{\n"
-        ".reg .pred p;\n"
+        ".reg .pred p, e;\n"
+        ".reg .b32 rx;\n"
+        "elect.sync rx|e, 0xffffffff;\n"
         "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d),
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
   else
     asm volatile(
         "{\n"
-        ".reg .pred p;\n"
+        ".reg .pred p, e;\n"
+        ".reg .b32 rx;\n"
+        "elect.sync rx|e, 0xffffffff;\n"
         "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d),
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// Arrive on `bar` when all MMAs issued so far by this thread have retired; for a pair, on that barrier in BOTH CTAs.
+// Arrive on `bar` when all MMAs issued so far by the elected lane have retired; for a pair, on that barrier in BOTH CTAs.
+// (elect.sync returns the same lane every time for a full mask, so the commit tracks the MMAs above.)
 template <int kCtas>
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   if (kCtas == 1)
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile(
+        "{\n.reg .pred e;\n.reg .b32 rx;\nelect.sync rx|e, 0xffffffff;\n"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(smem_u32(bar))
+        : "memory");
   else
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-                 "h"(uint16_t(3))
-                 : "memory");
+    asm volatile(
+        "{\n.reg .pred e;\n.reg .b32 rx;\nelect.sync rx|e, 0xffffffff;\n"
+        "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n}\n" ::"r"(smem_u32(bar)),
+        "h"(uint16_t(3))
+        : "memory");
 }
 __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -242,7 +256,7 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
   __syncthreads();
   if (kCtas == 2) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform: feeds the MMA's uniform registers
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer ------------------------------------------------
@@ -316,7 +330,8 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
         const int s = it % kStages;
         mbar_wait(&full[s], (it / kStages) & 1);
         tc_fence_after();
-        if (lane == 0) {
+        __syncwarp();
+        {   // all lanes, converged; one elected lane issues (see umma_f16)
           const uint32_t base = smem_u32(smem + s * kStageBytes);
           const uint64_t da_hi = umma_desc(base), da_lo = umma_desc(base + kABytes);
           const uint64_t db_hi = umma_desc(base + 2 * kABytes), db_lo = umma_desc(base + 2 * kABytes + nb * kRowBytes);
@@ -343,7 +358,8 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
         wait_shared(&a2_full[s], a2_cnt[s] & 1);
         ++a2_cnt[s];
         tc_fence_after();
-        if (lane == 0) {
+        __syncwarp();
+        {
           const uint32_t base = smem_u32(smem + s * kStageBytes);
           const uint64_t da_hi = umma_desc(base), da_lo = umma_desc(base + kABytes);
           const uint64_t db_hi = umma_desc(base + 2 * kABytes), db_lo = umma_desc(base + 2 * kABytes + (n2 / kCtas) * kRowBytes);

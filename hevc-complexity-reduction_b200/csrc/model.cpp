@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstring>
 
+#include "conv_tc.h"
 #include "kernels.h"
 
 namespace ethcnn {
@@ -80,8 +81,10 @@ bool pack_model(const std::map<std::string, BundleTensor>& t, float input_bound,
     return e;
   };
   out->conv.assign(kConvFloats, 0.f);
+  out->conv_tc.assign(kTcBlobBytes, 0);
   const int branch_base[3] = {12, 6, 0};  // S, M, L -> first Variable index (net_CNN.py:126-141)
   float feat_bound = 0.f;
+  const BundleTensor* bt[3][6] = {};
   for (int br = 0; br < 3; ++br) {
     const int v = branch_base[br];
     const BundleTensor* w1 = find(t, var_name(v), {4, 4, 1, 16}, err);
@@ -91,6 +94,7 @@ bool pack_model(const std::map<std::string, BundleTensor>& t, float input_bound,
     const BundleTensor* w3 = find(t, var_name(v + 4), {2, 2, 24, 32}, err);
     const BundleTensor* b3 = find(t, var_name(v + 5), {32}, err);
     if (!w1 || !b1 || !w2 || !b2 || !w3 || !b3) return false;
+    bt[br][0] = w1, bt[br][1] = b1, bt[br][2] = w2, bt[br][3] = b2, bt[br][4] = w3, bt[br][5] = b3;
     float* dst = out->conv.data() + br * kConvBranchFloats;
     memcpy(dst + kB1Off, b1->data.data(), 16 * 4);
     memcpy(dst + kB2Off, b2->data.data(), 24 * 4);
@@ -209,6 +213,31 @@ bool pack_model(const std::map<std::string, BundleTensor>& t, float input_bound,
     hdr[1] = std::ldexp(1.0f, -(e[1] + e[2]));            // conv2: A = c1 * 2^e_c1, B = w2 * 2^e2w
     hdr[2] = std::ldexp(1.0f, -(out->feat_exp + e[3]));   // conv3: A = c2 * 2^feat_exp, B = w3 * 2^e3w
     hdr[3] = std::ldexp(1.0f, e[1]);
+  }
+  // the same filters (same exponents, same hi/lo values) as 128-byte-swizzled K-major UMMA tiles for conv_tc.cu
+  for (int br = 0; br < 3; ++br) {
+    uint8_t* blob = out->conv_tc.data() + size_t(br) * kTcBranchBytes;
+    const int* e = out->conv_exp[br];
+    auto put = [&](int off_hi, int off_lo, int n, int k, float v) {   // element (row n, K index k) of a [..][64] tile
+      const size_t o = size_t(n >> 3) * 1024 + size_t(n & 7) * 128 + size_t(((k >> 3) ^ (n & 7)) << 4) + size_t(k & 7) * 2;
+      const uint16_t h = f32_to_f16_bits(v);
+      const uint16_t l = f32_to_f16_bits(v - f16_bits_to_f32(h));
+      memcpy(blob + off_hi + o, &h, 2);
+      memcpy(blob + off_lo + o, &l, 2);
+    };
+    const float s1 = std::ldexp(1.0f, e[0]), s2 = std::ldexp(1.0f, e[2]), s3 = std::ldexp(1.0f, e[3]);
+    for (int k = 0; k < 16; ++k)
+      for (int n = 0; n < 16; ++n) put(kTcW1Hi, kTcW1Lo, n, k, bt[br][0]->data[size_t(k) * 16 + n] * s1);
+    for (int k = 0; k < 64; ++k)
+      for (int n = 0; n < 24; ++n) put(kTcW2Hi, kTcW2Lo, n, k, bt[br][2]->data[size_t(k) * 24 + n] * s2);
+    for (int k = 0; k < 96; ++k)
+      for (int n = 0; n < 32; ++n) put(kTcW3Hi + (k >> 6) * 4096, kTcW3Lo + (k >> 6) * 4096, n, k & 63, bt[br][4]->data[size_t(k) * 32 + n] * s3);
+    float* tab = reinterpret_cast<float*>(blob + kTcTab);
+    const float sc1 = std::ldexp(1.0f, e[1]), fs = std::ldexp(1.0f, out->feat_exp);
+    const float* v4 = out->conv.data() + br * kConvBranchFloats;
+    for (int c = 0; c < 16; ++c) tab[c] = bt[br][1]->data[c] * sc1, tab[16 + c] = v4[kW1SumOff + c];
+    for (int c = 0; c < 24; ++c) tab[32 + c] = bt[br][3]->data[c] * fs;
+    for (int c = 0; c < 32; ++c) tab[56 + c] = bt[br][5]->data[c] * fs;
   }
   out->w_exp = pick_exp(wmax > 0.f ? wmax : 1.f);
   const float ws = std::ldexp(1.0f, out->w_exp);

@@ -14,6 +14,7 @@ namespace ethcnn {
 
 struct PackedModel {
   std::vector<float> conv;        // [3 branches S,M,L][kConvBranchFloats], see kernels.h
+  std::vector<uint8_t> conv_tc;   // [3 branches S,M,L][kTcBranchBytes]: the same filters as swizzled UMMA tiles, see conv_tc.h
   std::vector<float> w1;          // [2688][448] fp32, heads side by side (64 | 128 | 256)
   std::vector<float> b1;          // [448]
   std::vector<uint16_t> w1_hi;    // [448][2688] fp16 bits of w1 * 2^w_exp (K-major, for tcgen05)

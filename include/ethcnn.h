@@ -133,6 +133,7 @@ int ethcnn_decisions(ethcnn_handle* h, const float* prob, size_t n_ctus, const f
 #define ETHCNN_Q_FC1_PATH          3 /* dense path, see ETHCNN_OPT_FC1_PATH                           */
 #define ETHCNN_Q_TMA_LOADER_USED   4 /* 1 if the last device call used the TMA tile loader         */
 #define ETHCNN_Q_SM_COUNT          5
+#define ETHCNN_Q_CONV_PATH         6 /* conv stage, see ETHCNN_OPT_CONV_PATH                        */
 int ethcnn_query(ethcnn_handle* h, int what, int64_t* value);
 
 /* Per-kernel device timing: when enabled, every launch is bracketed by CUDA events on the launching
@@ -155,6 +156,8 @@ int ethcnn_profile_read(ethcnn_handle* h, int stage, double* ms_total, int64_t* 
                                     library-owned local buffer and the gate kernel copies the finished rows to d_out with
                                     coalesced stores: set it when d_out is PEER memory (ethcnn_peer_buffer_open), so that the
                                     rows cross NVLink as full 128-byte transactions.  0 (default) = rows are written in place */
+#define ETHCNN_OPT_CONV_PATH   4 /* 0 = conv stage on mma.sync (register-chained fragments), 1 = conv stage on tcgen05 with the
+                                    activations chained through tensor memory (needs the TMA tile loader; falls back to 0) */
 int ethcnn_set_option(ethcnn_handle* h, int option, int64_t value);
 
 /*

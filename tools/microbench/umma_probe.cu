@@ -38,16 +38,20 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 }
 __device__ __forceinline__ uint32_t idesc_f16(int n) { return (1u << 4) | (uint32_t(n >> 3) << 17) | (uint32_t(128 >> 4) << 24); }
 
+// Issued by ALL lanes of a converged warp with warp-uniform operands; elect.sync picks the one lane that really issues.
+// (Issuing from inside `if (lane == 0)` makes ptxas wrap every MMA in a divergence "waterfall" loop -- ELECT / R2UR.BROADCAST /
+// BRA.U.ANY -- that costs ~110 cycles per MMA: harmless under a 128-cycle N = 256 MMA, fatal for skinny ones.)
 __device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(a),
-               "l"(b), "r"(idesc), "r"(acc) : "memory");
+  asm volatile("{\n.reg .pred p, e;\n.reg .b32 rx;\nelect.sync rx|e, 0xffffffff;\nsetp.ne.b32 p, %4, 0;\n"
+               "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d),
-               "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc) : "memory");
+  asm volatile("{\n.reg .pred p, e;\n.reg .b32 rx;\nelect.sync rx|e, 0xffffffff;\nsetp.ne.b32 p, %4, 0;\n"
+               "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ void commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  asm volatile("{\n.reg .pred e;\n.reg .b32 rx;\nelect.sync rx|e, 0xffffffff;\n"
+               "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
 }
 
 constexpr int kK = 64;   // one swizzle row of fp16
@@ -58,7 +62,8 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int k) {
 }
 
 // mode 0 = SS, 1 = TS.  reps > 1: timing (D is then reps * A B^T).
-__global__ void __launch_bounds__(128, 1) probe(const __half* A, const __half* B, float* D, int N, int mode, int reps, long long* cycles) {
+__global__ void __launch_bounds__(128, 1) probe(const __half* A, const __half* B, float* D, int N, int mode, int reps, long long* cycles,
+                                                int nacc /* accumulators used round-robin (timing only) */) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                 // 16 KB
@@ -80,7 +85,7 @@ __global__ void __launch_bounds__(128, 1) probe(const __half* A, const __half* B
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem = *slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *slot, 0);
   const uint32_t lane_addr = uint32_t(warp * 32) << 16;
   constexpr uint32_t kACol = 256;     // A operand lives at columns 256 .. 287 (K = 64 fp16 = 32 columns)
   if (mode == 1) {
@@ -102,20 +107,30 @@ __global__ void __launch_bounds__(128, 1) probe(const __half* A, const __half* B
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
-  if (tid == 0) {
+  if (warp == 0) {   // the whole warp, converged
     const uint64_t da = umma_desc_sw128(smem_u32(sA)), db = umma_desc_sw128(smem_u32(sB));
     const uint32_t idesc = idesc_f16(N);
     const long long t0 = clock64();
-    for (int rep = 0; rep < reps; ++rep)
+    int acc = 0;         // nacc = 1: one accumulator, dependent MMAs; > 1: rotation over independent ones
+    if (mode == 0) {
+      for (int rep = 0; rep < reps; ++rep)
 #pragma unroll
-      for (int ks = 0; ks < kK / 16; ++ks) {
-        if (mode == 0) mma_ss(tmem, da + uint64_t(ks * 2), db + uint64_t(ks * 2), idesc, (rep | ks) != 0);
-        else mma_ts(tmem, tmem + kACol + ks * 8, db + uint64_t(ks * 2), idesc, (rep | ks) != 0);
-      }
+        for (int ks = 0; ks < kK / 16; ++ks) {
+          mma_ss(tmem + uint32_t(acc * N), da + uint64_t(ks * 2), db + uint64_t(ks * 2), idesc, (rep | ks) != 0);
+          acc = (acc + 1 == nacc) ? 0 : acc + 1;
+        }
+    } else {
+      for (int rep = 0; rep < reps; ++rep)
+#pragma unroll
+        for (int ks = 0; ks < kK / 16; ++ks) {
+          mma_ts(tmem + uint32_t(acc * N), tmem + kACol + ks * 8, db + uint64_t(ks * 2), idesc, (rep | ks) != 0);
+          acc = (acc + 1 == nacc) ? 0 : acc + 1;
+        }
+    }
     commit(bar);
     mbar_wait(bar, 0);
     const long long t1 = clock64();
-    if (cycles) *cycles = t1 - t0;
+    if (cycles && tid == 0) *cycles = t1 - t0;
   }
   __syncthreads();
   mbar_wait(bar, 0);
@@ -152,7 +167,7 @@ int main() {
   for (int mode = 0; mode < 2; ++mode)
     for (int N : Ns) {
       std::vector<float> hD(128 * N);
-      probe<<<1, 128, smem_bytes>>>(dA, dB, dD, N, mode, 1, dC);
+      probe<<<1, 128, smem_bytes>>>(dA, dB, dD, N, mode, 1, dC, 1);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) {
         printf("%s N=%d: CUDA error %s\n", mode ? "TS" : "SS", N, cudaGetErrorString(e));
@@ -168,12 +183,16 @@ int main() {
           if (d > maxerr) maxerr = d;
         }
       const int reps = 512;
-      long long cyc = 0;
-      probe<<<1, 128, smem_bytes>>>(dA, dB, dD, N, mode, reps, dC);
-      cudaDeviceSynchronize();
-      cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost);
-      printf("%s M=128 N=%3d K=16: max|err| = %g   %.1f cycles per MMA (%d back to back), %.0f MAC/clk\n", mode ? "TS" : "SS", N, maxerr,
-             double(cyc) / (reps * 4), reps * 4, 128.0 * N * 16 / (double(cyc) / (reps * 4)));
+      printf("%s M=128 N=%3d K=16: max|err| = %g; cycles per MMA (%d back to back) with 1/2/4/8 accumulators in rotation:", mode ? "TS" : "SS", N,
+             maxerr, reps * 4);
+      for (int nacc = 1; nacc <= 8 && nacc * N <= 256; nacc *= 2) {
+        long long cyc = 0;
+        probe<<<1, 128, smem_bytes>>>(dA, dB, dD, N, mode, reps, dC, nacc);
+        cudaDeviceSynchronize();
+        cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost);
+        printf("  %.1f", double(cyc) / (reps * 4));
+      }
+      printf("\n");
     }
   return 0;
 }
