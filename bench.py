@@ -249,6 +249,17 @@ def run_ours(args):
                 print("[bench] peer gather buffer unavailable (%s): NCCL gather instead" % peer.error, file=sys.stderr)
             peer = None
     peer_out = peer.row_ptr(rank * n_ctus) if peer is not None else 0
+    # e2e at N > 1: every rank's D2H lands in ONE page-locked shared host block at its row offset, so rank 0 owns the
+    # whole sequence's rows in host memory without a gather (falls back to H2D + NCCL gather + D2H if it cannot register)
+    host_rows = None
+    if world > 1 and not args.nccl_gather:
+        host_rows = eb.sharding.SharedHostRows(world * n_ctus, 21, dst=0)
+        ok = torch.tensor([1 if host_rows.registered else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            host_rows.close()
+            host_rows = None
+    host_out = host_rows.row_ptr(rank * n_ctus) if host_rows is not None else 0
 
     def barrier():
         if world > 1:
@@ -266,6 +277,9 @@ def run_ours(args):
 
     def step_e2e(i):
         k = i % 4
+        if host_rows is not None:   # the call's own D2H is the gather
+            net.predict_luma_ptr(clips_host[k].data_ptr(), W, H, W * H, FRAMES, QPS[k], host_out)
+            return
         net.predict_luma_ptr(clips_host[k].data_ptr(), W, H, W * H, FRAMES, QPS[k], out_host.data_ptr())
         if world > 1:
             out_dev.copy_(out_host, non_blocking=True)
@@ -348,6 +362,18 @@ def run_ours(args):
     e2e_ms = max_over_ranks(e2e_wall_ms)
     e2e_value = world * args.steps * n_ctus / (e2e_ms * 1e-3)
     clocks = sampler.stop()
+    e2e_check = None
+    if host_rows is not None:
+        # outside the timed region: rank 0's shared block must hold every rank's rows of the last e2e step
+        k = (args.steps - 1) % 4
+        net.predict_luma_device(clips_dev[k].data_ptr(), W, H, W, W * H, FRAMES, QPS[k], out_dev.data_ptr(), stream.cuda_stream)
+        dist.gather(out_dev, gather_buf, dst=0)
+        torch.cuda.synchronize()
+        if rank == 0:
+            same = bool(np.array_equal(host_rows.rows(), torch.cat(gather_buf).cpu().numpy()))
+            e2e_check = "rows in the shared host block are bit-identical to an NCCL gather" if same else "MISMATCH"
+            if not same:
+                raise SystemExit("shared host rows differ from the NCCL gather")
     total_launches = int(sum_over_ranks(launches))
 
     if rank == 0:
@@ -427,7 +453,10 @@ def run_ours(args):
                                       "fused tcgen05 FC1+FC2+FC3 on CTA pairs (cta_group::2)")[net.query(3)]},
             "e2e": {"value": e2e_value, "unit": "CTU/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": world * FRAMES * W * H, "d2h_bytes_per_step": world * n_ctus * 84,
-                    "timing": "wall clock between device-synchronised barriers, max over ranks"},
+                    "timing": "wall clock between device-synchronised barriers, max over ranks",
+                    "gather": (None if world == 1 else "every rank's D2H lands in one page-locked shared host block (no collective)"
+                               if host_rows is not None else "H2D + NCCL gather + D2H on rank 0"),
+                    "gather_check": e2e_check},
             "gpu_launches": total_launches,
             "clocks": clocks,
             "roofline": roofline,
@@ -440,6 +469,8 @@ def run_ours(args):
         print(json.dumps(line))
     if peer is not None:
         peer.close()
+    if host_rows is not None:
+        host_rows.close()
     net.close()
     if world > 1:
         dist.barrier()

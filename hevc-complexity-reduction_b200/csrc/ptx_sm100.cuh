@@ -32,12 +32,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// try_wait suspends in hardware for a bounded time per attempt; ~2^26 failed attempts is far beyond any
-// legitimate wait (seconds), so treat it as a deadlock and trap.
+// try_wait suspends in hardware for a bounded time per attempt; ~2^23 failed attempts is far beyond any
+// legitimate wait (the longest kernels here run for a few hundred microseconds), so treat it as a deadlock and trap.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if (++spins > (1u << 23)) __trap();
   }
 }
 
@@ -47,7 +47,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     __nanosleep(256);
-    if (++spins > (1u << 24)) __trap();
+    if (++spins > (1u << 21)) __trap();
   }
 }
 
@@ -83,7 +83,7 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait_cluster(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if (++spins > (1u << 23)) __trap();
   }
 }
 __device__ __forceinline__ void cluster_sync_all() {

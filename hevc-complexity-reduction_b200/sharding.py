@@ -151,6 +151,75 @@ class PeerGather(object):
         self.ok = False
 
 
+class SharedHostRows(object):
+    """The HOST-side twin of PeerGather for the host-pointer API (ethcnn_predict_luma): one POSIX shared-memory block
+    holds the whole sequence's rows, every rank maps it, page-locks it (cudaHostRegister, so the library's D2H copies go
+    straight into it) and passes `ptr + first_row_of_rank * 84` as the `out` pointer.  Rank dst then owns the complete
+    cu_depth rows in host memory without any gather: what video_to_cu_depth.py:114-116 writes out.  torch.distributed
+    only carries the block's name and the closing barrier."""
+
+    def __init__(self, total_rows: int, row_width: int = 21, dst: int = 0, group=None, register: bool = True):
+        import ctypes
+        from multiprocessing import shared_memory
+
+        import torch.distributed as dist
+
+        self.total_rows, self.row_width, self.dst, self.group = int(total_rows), int(row_width), dst, group
+        self.rank = dist.get_rank(group)
+        self.n_bytes = max(4, self.total_rows * self.row_width * 4)
+        box = [None]
+        if self.rank == dst:
+            self.shm = shared_memory.SharedMemory(create=True, size=self.n_bytes)
+            box[0] = self.shm.name
+        dist.broadcast_object_list(box, src=dst, group=group)
+        if self.rank != dst:
+            self.shm = shared_memory.SharedMemory(name=box[0])
+        self._view = (ctypes.c_char * self.n_bytes).from_buffer(self.shm.buf)
+        self.ptr = ctypes.addressof(self._view)
+        self.registered = False
+        if register:
+            import torch
+
+            if torch.cuda.is_available():
+                rc = torch.cuda.cudart().cudaHostRegister(self.ptr, self.n_bytes, 0)
+                self.registered = int(rc) == 0
+        dist.barrier(group=group)
+
+    def row_ptr(self, first_row: int) -> int:
+        if not 0 <= first_row <= self.total_rows:
+            raise ValueError("row outside the shared block")
+        return self.ptr + int(first_row) * self.row_width * 4
+
+    def rows(self):
+        """Rank dst: numpy view [total_rows, row_width] of the block (valid after every rank's call returned and a barrier)."""
+        import numpy as np
+
+        if self.rank != self.dst:
+            return None
+        return np.frombuffer(self.shm.buf, dtype="<f4", count=self.total_rows * self.row_width).reshape(-1, self.row_width)
+
+    def close(self) -> None:
+        """Collective: every rank calls it."""
+        import torch.distributed as dist
+
+        if self.registered:
+            import torch
+
+            torch.cuda.cudart().cudaHostUnregister(self.ptr)
+            self.registered = False
+        dist.barrier(group=self.group)
+        self._view = None
+        try:
+            self.shm.close()
+        except BufferError:
+            pass   # a numpy view handed out by rows() is still alive; the mapping goes with the process
+        if self.rank == self.dst:
+            try:
+                self.shm.unlink()
+            except FileNotFoundError:
+                pass
+
+
 def predict_sharded(predict_frames: Callable[[int, int], "object"], n_frames: int, rows_per_frame: int,
                     row_width: int = 21, dst: int = 0, group=None):
     """Run `predict_frames(first_frame, n)` (returns this rank's rows as a torch tensor) on this rank's

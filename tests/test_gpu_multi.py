@@ -58,6 +58,17 @@ def _worker(rank, world, port, model_dir, n_frames, out_dir):
         np.save(os.path.join(out_dir, "peer.npy"), pg.rows().cpu().numpy())
     pg.close()
 
+    # (a') host-pointer API: every rank's D2H lands in one shared, page-locked host block
+    hr = eb.sharding.SharedHostRows(n_frames * rows_per_frame, 21, dst=0)
+    assert hr.registered
+    if nf:
+        host_luma = torch.from_numpy(_clip(n_frames)[f0:f0 + nf].copy()).pin_memory()
+        net.predict_luma_ptr(host_luma.data_ptr(), W, H, W * H, nf, QP, hr.row_ptr(f0 * rows_per_frame))
+    dist.barrier()
+    if rank == 0:
+        np.save(os.path.join(out_dir, "host.npy"), hr.rows().copy())
+    hr.close()
+
     # (b) the collective
     net.set_option(eb.OPT_STAGED_OUTPUT, 0)
     local = torch.empty((nf * rows_per_frame, 21), dtype=torch.float32, device=dev)
@@ -85,6 +96,7 @@ def test_peer_gather_and_nccl_gather_equal_single_gpu(eb, ai_model_dir, tmp_path
         want = net.predict_luma(_clip(n_frames), W, H, n_frames, QP)
     assert np.array_equal(np.load(tmp_path / "peer.npy"), want)
     assert np.array_equal(np.load(tmp_path / "nccl.npy"), want)
+    assert np.array_equal(np.load(tmp_path / "host.npy"), want)
 
 
 def test_staged_output_is_bit_identical(eb, ai_model_dir):

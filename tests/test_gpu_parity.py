@@ -257,6 +257,26 @@ def test_pinned_and_pageable_hosts_agree(eb, ai_model_dir):
         assert np.array_equal(out.numpy(), a)
 
 
+def test_tcgen05_conv_stage_is_bit_identical_to_the_mma_sync_stage(eb, ai_model_dir):
+    """ETHCNN_OPT_CONV_PATH = 1 (conv_tc.cu: tcgen05 MMAs, activations chained through tensor memory) computes the same
+    products with the same fp32 accumulation as the default conv stage: features and probabilities agree bit for bit,
+    including partial tasks (CTU counts that are not multiples of 8 / 32 / 128) and zero-padded frame edges."""
+    d, _ = ai_model_dir
+    for (W, H, nf) in ((64, 64, 1), (200, 136, 5), (1920, 1080, 3)):
+        luma = np.stack([eo.synth_frame(W, H, 40 + k) for k in range(nf)])
+        r, c = eb.ctu_grid(W, H)
+        res = []
+        for path in (0, 1):
+            with eb.EthCnn(d, None, eb.MODE_AI, device=0) as n:      # a handle per path: fresh (zeroed) feature buffers
+                n.set_option(eb.OPT_CONV_PATH, path)
+                assert n.query(eb.Q_CONV_PATH) == path
+                prob = n.predict_luma(luma, W, H, nf, 32)
+                res.append((prob, n.debug_read_scratch(0, nf * r * c)))
+        assert np.abs(res[0][1]).max() > 1.0
+        assert np.array_equal(res[0][1], res[1][1]), "conv features differ (%dx%d)" % (W, H)
+        assert np.array_equal(res[0][0], res[1][0])
+
+
 def test_first_call_on_a_fresh_handle_is_clean(eb, ai_model_dir):
     """Regression: the one-off zero fill of the feature buffers and the weight upload happen inside the FIRST call of a
     handle (what the CLI does every run) and used to race with that call's kernels on the non-blocking streams (the lo

@@ -152,6 +152,45 @@ def test_peer_gather_equals_single_process(tmp_path, world, n_frames, fail_rank)
     assert got.shape == want.shape and np.array_equal(got, want)
 
 
+def _host_rows_worker(rank, world, port, n_frames, out_path):
+    import ctypes
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import ethcnn_b200 as eb
+    from oracle import ethcnn_oracle as eo
+
+    torch.set_num_threads(1)
+    W, H, rows_per_frame = 200, 136, 12
+    yuv = eo.synth_yuv(W, H, n_frames, seed0=50)
+    fb = W * H * 3 // 2
+    f0, nf = eb.sharding.frame_range(n_frames, world, rank)
+    hr = eb.sharding.SharedHostRows(n_frames * rows_per_frame, 21, dst=0, register=False)
+    if nf:   # "ethcnn_predict_luma(..., out = hr.row_ptr(first row of this rank))"
+        local = np.ascontiguousarray(eo.get_prob(yuv[f0 * fb:(f0 + nf) * fb], W, H, 32, eo.random_weights(3), eo.MODE_AI, (0.5, 0.5)), "<f4")
+        ctypes.memmove(hr.row_ptr(f0 * rows_per_frame), local.ctypes.data, local.nbytes)
+    dist.barrier()
+    if rank == 0:
+        eb.sharding.write_cu_depth(out_path, hr.rows().copy())
+    else:
+        assert hr.rows() is None
+    hr.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_frames", [(2, 5), (3, 2)])
+def test_shared_host_rows_equal_single_process(tmp_path, world, n_frames):
+    from oracle import ethcnn_oracle as eo
+
+    out = str(tmp_path / "cu_depth.dat")
+    mp.spawn(_host_rows_worker, args=(world, _free_port(), n_frames, out), nprocs=world, join=True)
+    W, H = 200, 136
+    want = eo.get_prob(eo.synth_yuv(W, H, n_frames, seed0=50), W, H, 32, eo.random_weights(3), eo.MODE_AI, (0.5, 0.5))
+    got = np.fromfile(out, dtype="<f4").reshape(-1, 21)
+    assert got.shape == want.shape and np.array_equal(got, want)
+
+
 def test_frame_ranges(eb):
     fr = eb.sharding.all_frame_ranges
     assert [n for _, n in fr(50, 8)] == [7, 7, 6, 6, 6, 6, 6, 6]          # BASELINE config 3
