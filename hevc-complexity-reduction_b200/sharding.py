@@ -174,6 +174,12 @@ class SharedHostRows(object):
         dist.broadcast_object_list(box, src=dst, group=group)
         if self.rank != dst:
             self.shm = shared_memory.SharedMemory(name=box[0])
+            try:   # only the creator owns (and unlinks) the block; keep this process's resource tracker out of it
+                from multiprocessing import resource_tracker
+
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
         self._view = (ctypes.c_char * self.n_bytes).from_buffer(self.shm.buf)
         self.ptr = ctypes.addressof(self._view)
         self.registered = False
