@@ -43,9 +43,9 @@ FC1_FLOP_PER_CTU = 2 * 1204224
 CONV_FLOP_PER_CTU = 2 * 279552
 FP32_FFMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal, not measured
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch over 25 500 CTUs, from the `ncu --set full` captures
-# summarised in profiles/r01f_conv_v4.md (conv) and profiles/r01e_fc_pair.md (fused FC), per CTU
-NCU_DRAM_BYTES_PER_CTU = {"conv": (104.528640e6 + 224.208384e6) / 25500, "fc1": (289.939456e6 + 5.607680e6) / 25500}
-NCU_DRAM_SOURCE = {"conv": "profiles/r01f_conv_v4.md", "fc1": "profiles/r01e_fc_pair.md"}
+# summarised in profiles/r01h_conv_v4.md (conv) and profiles/r01h_fc_pair.md (fused FC), per CTU
+NCU_DRAM_BYTES_PER_CTU = {"conv": (104.451328e6 + 223.326720e6) / 25500, "fc1": (290.425600e6 + 5.473792e6) / 25500}
+NCU_DRAM_SOURCE = {"conv": "profiles/r01h_conv_v4.md", "fc1": "profiles/r01h_fc_pair.md"}
 
 
 def make_clip(seed0: int, n_base: int = 5) -> np.ndarray:

@@ -166,6 +166,37 @@ def test_full_size_config2_and_config3_frames_vs_oracle(net):
         check(got, want, what="%dx%d" % (W, H))
 
 
+@pytest.mark.parametrize("name,W,H,nf,qp,mode", [
+    ("config3", 4928, 3264, 50, 32, "AI"),     # 196 350 CTUs, 804 MB of luma, sub-batches 1024/1024/1024/855
+    ("config4", 2880, 1920, 425, 27, "AI"),    # 573 750 CTUs, 2.35 GB of luma, sub-batches 1024/326, 16 feature chunks
+    ("config5", 1920, 1080, 240, 37, "LDP"),   # 122 400 CTUs of residue frames, LDP weights, no gates
+])
+def test_baseline_full_size_sequences(eb, ai_model_dir, ldp_model_dir, name, W, H, nf, qp, mode):
+    """BASELINE.json configs 3-5 at their full sizes through the host API (pageable source, slabs, feature chunks that
+    start and end inside frames).  Size-independent properties: the sequence cycles over five base frames, so every
+    repetition of a base frame must reproduce its rows bit for bit wherever it falls; rows are probabilities; and the
+    first cycle equals the oracle on those five frames (the only part the oracle has to compute)."""
+    d, present = ai_model_dir if mode == "AI" else ldp_model_dir
+    model = assets.AI_MODELS[qp] if mode == "AI" else assets.LDP_MODEL
+    if model not in present:
+        pytest.skip("%s not on this box" % model)
+    make = eo.synth_frame if mode == "AI" else eo.synth_residue_frame
+    base = np.stack([make(W, H, 900 + k) for k in range(5)])
+    clip = np.tile(base, (nf // 5, 1, 1))
+    assert clip.shape[0] == nf
+    r, c = eb.ctu_grid(W, H)
+    n = r * c
+    with eb.EthCnn(d, None, eb.MODE_AI if mode == "AI" else eb.MODE_LDP, device=0) as net:
+        got = net.predict_luma(clip, W, H, nf, qp).reshape(nf // 5, 5 * n, 21)
+    assert np.isfinite(got).all() and got.min() >= 0 and got.max() <= 1
+    for k in range(1, nf // 5):
+        assert np.array_equal(got[k], got[0]), "%s: repetition %d differs" % (name, k)
+    w = assets.load_weights(model)
+    yuv = b"".join(f.tobytes() + bytes([128]) * (W * H // 2) for f in base)
+    want = eo.get_prob(yuv, W, H, qp, w, eo.MODE_AI if mode == "AI" else eo.MODE_LDP, (0.5, 0.5) if mode == "AI" else None)
+    check(got[0], want, what=name)
+
+
 def test_flat_and_noise_frames(net):
     """Degenerate content: a flat frame closes both gates, uniform noise saturates."""
     w = assets.load_weights(assets.AI_MODELS[32])

@@ -64,6 +64,7 @@ def write_launches(tag, path_csv):
     hdr = rows[0]
     ki, vi, gi, bi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size"), hdr.index("Block Size")
     agg = collections.OrderedDict()
+    per_kernel = collections.OrderedDict()
     for r in rows[1:]:
         try:
             v = float(r[vi].replace(",", ""))
@@ -72,6 +73,7 @@ def write_launches(tag, path_csv):
         a = agg.setdefault(r[ki], [0, 0.0, r[gi], r[bi]])
         a[0] += 1
         a[1] += v
+        per_kernel.setdefault(r[ki], []).append(v)
     tot = sum(a[1] for a in agg.values())
     path = os.path.join(ROOT, "profiles", "%s_launches.md" % tag)
     with open(path, "w") as f:
@@ -81,6 +83,15 @@ def write_launches(tag, path_csv):
                 "| kernel | launches | mean us | total us | share | grid (first) | block |\n|---|---|---|---|---|---|---|\n" % os.path.basename(path_csv))
         for k, (n, t, g, b) in agg.items():
             f.write("| `%s` | %d | %.1f | %.1f | %.3f | %s | %s |\n" % (k[:90], n, t / n / 1e3, t / 1e3, t / tot, g, b))
+        # The command also runs the end-to-end arm, whose launches work on 8-frame slabs.  The device-resident steps
+        # (one launch per kernel over all 25 500 CTUs) are the longest launches of each kernel: their shares are what
+        # bench.py's `stages` report.
+        big = collections.OrderedDict((k, [v for v in vs if v >= 0.5 * max(vs)]) for k, vs in per_kernel.items())
+        tot_big = sum(sum(v) / len(v) for v in big.values())
+        f.write("\n## whole-step launches only (duration >= half of the kernel's longest launch)\n\n"
+                "| kernel | launches | mean us | share of the step |\n|---|---|---|---|\n")
+        for k, vs in big.items():
+            f.write("| `%s` | %d | %.1f | %.3f |\n" % (k[:60], len(vs), sum(vs) / len(vs) / 1e3, sum(vs) / len(vs) / tot_big))
     print("wrote", path)
 
 
