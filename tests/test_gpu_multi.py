@@ -110,14 +110,16 @@ def test_staged_output_is_bit_identical(eb, ai_model_dir):
     dev = torch.device("cuda", 0)
     luma = torch.from_numpy(frames).to(dev)
     n = 3 * 96
-    with eb.EthCnn(d, None, eb.MODE_AI, device=0) as net:
-        a = torch.full((n + 1, 21), -1.0, dtype=torch.float32, device=dev)
-        b = torch.full((n + 1, 21), -1.0, dtype=torch.float32, device=dev)
-        s = torch.cuda.current_stream().cuda_stream
-        net.predict_luma_device(luma.data_ptr(), W, H, W, W * H, 3, QP, a.data_ptr() + 84, s)
-        net.set_option(eb.OPT_STAGED_OUTPUT, 1)
-        net.predict_luma_device(luma.data_ptr(), W, H, W, W * H, 3, QP, b.data_ptr() + 84, s)
-        torch.cuda.synchronize()
-        a, b = a.cpu().numpy(), b.cpu().numpy()
-    assert np.array_equal(a, b)
-    assert (a[0] == -1).all() and (a[97:193, 1:] == 0).all() and (a[1:97, 0] > 0).all()
+    for fc_path in (3, 2, 1, 0):   # every dense path feeds the export kernel the same way
+        with eb.EthCnn(d, None, eb.MODE_AI, device=0) as net:
+            net.set_option(eb.OPT_FC1_PATH, fc_path)
+            a = torch.full((n + 1, 21), -1.0, dtype=torch.float32, device=dev)
+            b = torch.full((n + 1, 21), -1.0, dtype=torch.float32, device=dev)
+            s = torch.cuda.current_stream().cuda_stream
+            net.predict_luma_device(luma.data_ptr(), W, H, W, W * H, 3, QP, a.data_ptr() + 84, s)
+            net.set_option(eb.OPT_STAGED_OUTPUT, 1)
+            net.predict_luma_device(luma.data_ptr(), W, H, W, W * H, 3, QP, b.data_ptr() + 84, s)
+            torch.cuda.synchronize()
+            a, b = a.cpu().numpy(), b.cpu().numpy()
+        assert np.array_equal(a, b), "fc path %d" % fc_path
+        assert (a[0] == -1).all() and (a[97:193, 1:] == 0).all() and (a[1:97, 0] > 0).all()
