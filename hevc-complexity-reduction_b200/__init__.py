@@ -29,6 +29,8 @@ from .binding import (  # noqa: F401
     library_path,
     load_library,
     ctu_grid,
+    request,
+    request_quit,
 )
 from . import video_to_cu_depth, net_CNN, sharding  # noqa: F401
 

@@ -64,6 +64,10 @@ def load_library() -> C.CDLL:
         "ethcnn_peer_buffer_create": (i32, [vp, sz, C.POINTER(vp), vp]),
         "ethcnn_peer_buffer_open": (i32, [vp, vp, C.POINTER(vp)]),
         "ethcnn_peer_buffer_release": (i32, [vp, vp]),
+        "ethcnn_serve": (i32, [vp, cp, i32, i32]),
+        "ethcnn_request": (i32, [cp, cp, i32, i32, i32, cp]),
+        "ethcnn_request_quit": (i32, [cp]),
+        "ethcnn_request_error": (cp, []),
         "ethcnn_alloc_pinned": (vp, [sz]),
         "ethcnn_free_pinned": (None, [vp]),
         "ethcnn_debug_pack_model": (i32, [cp, C.c_float, vp, vp, vp, vp, vp, vp, vp]),
@@ -91,6 +95,23 @@ def ctu_grid(width: int, height: int) -> Tuple[int, int]:
 
 def _ptr(a: np.ndarray) -> C.c_void_p:
     return C.c_void_p(a.ctypes.data)
+
+
+def request(socket_path: str, yuv_path: str, width: int, height: int, qp: int, out_path: str = "cu_depth.dat") -> bool:
+    """Client of the resident server (include/ethcnn.h, ethcnn_request): True when the server did the work, False when
+    nobody listens on socket_path (the caller then works in-process); raises EthCnnError when the server failed."""
+    lib = load_library()
+    rc = lib.ethcnn_request(os.fsencode(socket_path), os.fsencode(yuv_path), width, height, qp, os.fsencode(out_path))
+    if rc == 0:
+        return True
+    msg = lib.ethcnn_request_error().decode("utf-8", "replace")
+    if rc == -2 and "no server" in msg:
+        return False
+    raise EthCnnError(rc, "server: " + msg)
+
+
+def request_quit(socket_path: str) -> bool:
+    return load_library().ethcnn_request_quit(os.fsencode(socket_path)) == 0
 
 
 class EthCnn(object):
@@ -206,6 +227,13 @@ class EthCnn(object):
         rc = self._lib.ethcnn_ldp_serve(self._h, os.fsencode(directory), max_frames, idle_timeout_ms)
         if rc < 0:
             _check(rc)
+        return rc
+
+    def serve(self, socket_path: str, max_requests: int = 0, idle_timeout_ms: int = 0) -> int:
+        """The resident All-Intra server loop (include/ethcnn.h, ethcnn_serve); returns the number of requests served."""
+        rc = self._lib.ethcnn_serve(self._h, os.fsencode(socket_path), max_requests, idle_timeout_ms)
+        if rc < 0:
+            raise EthCnnError(rc, "cannot serve on %s" % socket_path)
         return rc
 
     def decisions(self, prob: np.ndarray, thr6=(0.5,) * 6) -> np.ndarray:

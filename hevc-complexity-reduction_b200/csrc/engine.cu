@@ -44,6 +44,18 @@ int fail(int code, const std::string& msg) {
   return code;
 }
 
+// ETHCNN_TRACE=1: wall-clock milestones of a call on stderr (where does a one-shot CLI run spend its time?)
+void trace(const char* what) {
+  static const bool on = getenv("ETHCNN_TRACE") != nullptr;
+  if (!on) return;
+  static const auto t0 = std::chrono::steady_clock::now();
+  static auto last = t0;
+  const auto now = std::chrono::steady_clock::now();
+  fprintf(stderr, "[ethcnn %8.1f ms  +%7.1f] %s\n", std::chrono::duration<double, std::milli>(now - t0).count(),
+          std::chrono::duration<double, std::milli>(now - last).count(), what);
+  last = now;
+}
+
 #define CUDA_TRY(expr)                                                                                   \
   do {                                                                                                   \
     cudaError_t e__ = (expr);                                                                            \
@@ -229,12 +241,15 @@ int get_model(ethcnn_handle* h, DeviceCtx& c, int qp, DeviceModel** out) {
   std::map<std::string, BundleTensor> tensors;
   std::string err;
   const std::string path = h->model_dir.empty() ? prefix : h->model_dir + "/" + prefix;
+  trace("get_model: start");
   if (!read_tf_bundle(path, &tensors, &err)) {
     const bool io = err.find("cannot open") != std::string::npos;
     return fail(io ? ETHCNN_E_IO : ETHCNN_E_FORMAT, err);
   }
   PackedModel pm;
+  trace("get_model: checkpoint read");
   if (!pack_model(tensors, h->mode == ETHCNN_MODE_LDP ? 10.0f : 1.0f, &pm, &err)) return fail(ETHCNN_E_FORMAT, path + ": " + err);
+  trace("get_model: packed");
   DeviceModel m;
   int rc;
   if ((rc = upload(&m.conv, pm.conv.data(), pm.conv.size() * 4))) return rc;
@@ -281,6 +296,7 @@ int get_model(ethcnn_handle* h, DeviceCtx& c, int qp, DeviceModel** out) {
     return fail(ETHCNN_E_CUDA, std::string("fused FC weight tensor maps: ") + terr);
   // cudaMemcpy from pageable memory may return before the DMA has landed, and the kernels run on non-blocking streams
   CUDA_TRY(cudaDeviceSynchronize());
+  trace("get_model: uploaded");
   auto ins = c.models.emplace(prefix, m);
   *out = &ins.first->second;
   return ETHCNN_OK;
@@ -288,6 +304,7 @@ int get_model(ethcnn_handle* h, DeviceCtx& c, int qp, DeviceModel** out) {
 
 int ensure_scratch(ethcnn_handle* h, DeviceCtx& c, size_t flags_needed) {
   if (c.chunk_ctus != h->chunk_ctus || !c.feat_hi) {
+    trace("ensure_scratch: start");
     cudaFree(c.feat_hi), cudaFree(c.feat_lo), cudaFree(c.fc1);
     c.feat_hi = c.feat_lo = nullptr, c.fc1 = nullptr;
     c.chunk_ctus = h->chunk_ctus;
@@ -302,6 +319,7 @@ int ensure_scratch(ethcnn_handle* h, DeviceCtx& c, size_t flags_needed) {
     // The fills run on the legacy stream, which does NOT order against the non-blocking streams the kernels use:
     // without this the zero fill of a fresh handle's buffers could land on top of the first slab's features.
     CUDA_TRY(cudaDeviceSynchronize());
+    trace("ensure_scratch: feature buffers allocated + zeroed");
   }
   if (flags_needed > c.flags_cap) {
     cudaFree(c.flags);
@@ -623,8 +641,10 @@ int run_host_pipeline(ethcnn_handle* h, DeviceCtx& c, const uint8_t* y, int widt
   if (n_frames > 1 && slab_frames > (n_frames + 2) / 3) slab_frames = (n_frames + 2) / 3;
   const bool src_pinned = is_pinned(y);
   const bool dst_pinned = is_pinned(out);
+  trace("host pipeline: start");
   int rc = ensure_staging(c, dev_frame * slab_frames, size_t(slab_frames) * ctus_per_frame * per_ctu, !src_pinned, !dst_pinned);
   if (rc) return rc;
+  trace("host pipeline: staging buffers ready");
 
   struct Pending {
     int slab = -1, f0 = 0, nf = 0;
@@ -674,6 +694,7 @@ int run_host_pipeline(ethcnn_handle* h, DeviceCtx& c, const uint8_t* y, int widt
   }
   for (int b = 0; b < DeviceCtx::kSlabs; ++b)
     if ((rc = drain(b))) return rc;
+  trace("host pipeline: all slabs done");
   return ETHCNN_OK;
 }
 
@@ -863,14 +884,17 @@ bool write_all(const std::string& path, const void* src, size_t bytes) {
 
 int open_device(ethcnn_handle* h, int device) {
   int count = 0;
+  trace("open_device: start");
   if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
     cudaGetLastError();
     return fail(ETHCNN_E_CUDA, "no CUDA device available (this library has no CPU fallback)");
   }
   if (device < 0 || device >= count) return fail(ETHCNN_E_ARG, "CUDA device " + std::to_string(device) + " does not exist");
+  trace("open_device: driver initialised (cudaGetDeviceCount)");
   CUDA_TRY(cudaSetDevice(device));
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  trace("open_device: device selected");
   if (prop.major != 10) return fail(ETHCNN_E_CUDA, std::string("device is ") + prop.name + " (sm_" + std::to_string(prop.major) +
                                                         std::to_string(prop.minor) + "); this build targets sm_100a only");
   std::unique_ptr<DeviceCtx> c(new DeviceCtx());
@@ -884,6 +908,7 @@ int open_device(ethcnn_handle* h, int device) {
   CUDA_TRY(fc1_tc_configure());
   CUDA_TRY(heads_configure());
   CUDA_TRY(fc_fused_configure());
+  trace("open_device: context + streams + kernel attributes");
   h->devs.push_back(std::move(c));
   return ETHCNN_OK;
 }
@@ -965,8 +990,10 @@ int ethcnn_create_on_device(const char* model_dir, const char* thr_path, int mod
 
 void ethcnn_destroy(ethcnn_handle* h) {
   if (!h) return;
+  trace("destroy: start");
   for (auto& c : h->devs) close_device(*c);
   delete h;
+  trace("destroy: done");
 }
 
 int ethcnn_predict_luma_device(ethcnn_handle* h, const uint8_t* d_y, int width, int height, size_t pitch, size_t frame_stride,
@@ -1025,6 +1052,7 @@ int ethcnn_predict_yuv_file(ethcnn_handle* h, const char* yuv_path, int width, i
     madvise(mp, file_bytes, MADV_SEQUENTIAL);
     base = static_cast<const uint8_t*>(mp);
   }
+  trace("predict_yuv_file: file mapped");
   const size_t ctus = size_t((width + kCtu - 1) / kCtu) * ((height + kCtu - 1) / kCtu);
   std::vector<float> prob(n_frames * ctus * kProbs);
   int rc;
@@ -1035,6 +1063,7 @@ int ethcnn_predict_yuv_file(ethcnn_handle* h, const char* yuv_path, int width, i
   if (base) munmap(const_cast<uint8_t*>(base), file_bytes);
   close(fd);
   if (rc) return rc;
+  trace("predict_yuv_file: probabilities on the host");
   // single write at the end (video_to_cu_depth.py:114-116), via a temporary so failures leave no partial file
   const std::string tmp = std::string(out_path) + ".tmp." + std::to_string(getpid());
   FILE* f = fopen(tmp.c_str(), "wb");
@@ -1049,6 +1078,7 @@ int ethcnn_predict_yuv_file(ethcnn_handle* h, const char* yuv_path, int width, i
     remove(tmp.c_str());
     return fail(ETHCNN_E_IO, std::string("cannot rename onto ") + out_path);
   }
+  trace("predict_yuv_file: cu_depth.dat written");
   return ETHCNN_OK;
 }
 

@@ -48,6 +48,9 @@ def get_prob(yuv_name, image_size, save_file, qp_seq, n_frames_start, n_frames_e
         raise ValueError("only whole-file prediction is supported (as the reference script does)")
     if n_gpus is None:
         n_gpus = int(os.environ.get("ETHCNN_GPUS", "1") or "1")
+    server = os.environ.get("ETHCNN_SERVER", "")
+    if server and b.request(server, yuv_name, frame_width, frame_height, qp_seq, save_file):
+        return   # a resident server (video_to_cu_depth --serve) did it: no CUDA start-up in this process
     with b.EthCnn(model_dir, None, b.MODE_AI, n_gpus=n_gpus) as net:
         net.predict_yuv_file(yuv_name, frame_width, frame_height, qp_seq, save_file)
 

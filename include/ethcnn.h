@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define ETHCNN_ABI_VERSION 2 /* 2: staged output option + peer gather buffers */
+#define ETHCNN_ABI_VERSION 3 /* 2: staged output option + peer gather buffers; 3: resident server */
 
 /* Which network/deployment is evaluated. */
 #define ETHCNN_MODE_AI  0 /* HM-16.5_Test_AI/bin/net_CNN.py:103-195 (x/255, qp/51, batch-level gates)      */
@@ -121,6 +121,22 @@ int ethcnn_ldp_step(ethcnn_handle* h, const uint8_t* y, int width, int height, i
  * been served or nothing arrived for idle_timeout_ms (> 0); with both <= 0 it serves forever like the reference.
  */
 int ethcnn_ldp_serve(ethcnn_handle* h, const char* dir, int max_frames, int idle_timeout_ms);
+
+/*
+ * Resident server for the All-Intra drop-in.  HM starts the predictor afresh for every encode (TAppEncCfg.cpp:2317-2321) and a
+ * fresh process pays 2 - 4 s of CUDA initialisation before ~0.1 s of work; the reference solves the same start-up problem of
+ * TensorFlow with a resident daemon for its inter-mode path (README.md:64-84).  ethcnn_serve keeps the handle (context, packed
+ * weights, scratch) alive and answers requests on a Unix-domain stream socket until max_requests (> 0) PREDICT requests have
+ * been served, nothing arrived for idle_timeout_ms (> 0) or a client asked it to quit; returns the number of requests served
+ * (>= 0) or a negative code.  It uses the checkpoints / Thr_info.txt of the directory the handle was created with; relative
+ * paths of a request are resolved against the CLIENT's working directory.  Protocol: csrc/serve.cpp.
+ * ethcnn_request is the client (no handle, no CUDA): returns the server's code for ethcnn_predict_yuv_file, or ETHCNN_E_IO when
+ * nobody listens on socket_path (the CLI and the Python shim then work in-process); ethcnn_request_error() has the message.
+ */
+int ethcnn_serve(ethcnn_handle* h, const char* socket_path, int max_requests, int idle_timeout_ms);
+int ethcnn_request(const char* socket_path, const char* yuv_path, int width, int height, int qp, const char* out_path);
+int ethcnn_request_quit(const char* socket_path);
+const char* ethcnn_request_error(void);
 
 /* HM's use of a probability (TLibEncoder/TEncCu.cpp:448-462): 2 = split only (p > up), 0 = no split
  * (p <= down), 1 = check both.  thr6 = the six numbers of Thr_info.txt (up,down per depth,

@@ -4,6 +4,7 @@ identical HM decisions after threshold quantisation; every flip would be listed 
 import glob
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -251,6 +252,55 @@ def test_yuv_file_entry_point_and_cli(eb, ai_model_dir, tmp_path):
     os.remove(os.path.join(d, "cu_depth.dat"))
     r = subprocess.run(["python", script, str(tmp_path / "bad.yuv"), str(W), str(H), str(qp)], cwd=d, capture_output=True)
     assert r.returncode != 0 and not os.path.exists(os.path.join(d, "cu_depth.dat"))
+
+
+def test_resident_server_serves_the_drop_in(eb, ai_model_dir, tmp_path):
+    """`video_to_cu_depth --serve <socket>` keeps the CUDA context and the weights alive; the CLI and the Python shim become
+    clients when ETHCNN_SERVER names the socket (paths relative to the CLIENT's cwd) and produce the same bytes as working
+    in-process -- without paying for CUDA start-up in the client."""
+    import time
+
+    d, _ = ai_model_dir
+    cli = os.path.join(ROOT, "hevc-complexity-reduction_b200", "bin", "video_to_cu_depth")
+    shim = os.path.join(ROOT, "hevc-complexity-reduction_b200", "video_to_cu_depth.py")
+    W, H, nf, qp = 200, 136, 3, 32
+    work = tmp_path / "encoder_cwd"
+    work.mkdir()
+    (work / "clip.yuv").write_bytes(eo.synth_yuv(W, H, nf, seed0=7))
+    with eb.EthCnn(d, None, eb.MODE_AI, device=0) as net:
+        net.predict_yuv_file(str(work / "clip.yuv"), W, H, qp, str(work / "want.dat"))
+    want = (work / "want.dat").read_bytes()
+    sock = str(tmp_path / "ethcnn.sock")
+    srv = subprocess.Popen([cli, "--serve", sock], cwd=d, stderr=subprocess.PIPE)
+    try:
+        for _ in range(600):
+            if os.path.exists(sock) or srv.poll() is not None:
+                break
+            time.sleep(0.05)
+        assert os.path.exists(sock), "server did not come up"
+        env = dict(os.environ, ETHCNN_SERVER=sock, PYTHONPATH=ROOT)
+        for cmd in ([cli, "clip.yuv", str(W), str(H), str(qp)], [sys.executable, shim, "clip.yuv", str(W), str(H), str(qp)]):
+            out = work / "cu_depth.dat"
+            if out.exists():
+                out.unlink()
+            t = time.time()
+            r = subprocess.run(cmd, cwd=str(work), env=env, capture_output=True)
+            dt = time.time() - t
+            assert r.returncode == 0, r.stderr.decode()
+            assert out.read_bytes() == want
+            assert b"in-process" not in r.stderr
+        assert dt < 5.0
+        # a bad request is the server's error, not a crash; the server keeps serving
+        (work / "bad.yuv").write_bytes(b"123")
+        r = subprocess.run([cli, "bad.yuv", str(W), str(H), str(qp)], cwd=str(work), env=env, capture_output=True)
+        assert r.returncode == 1 and b"whole number" in r.stderr
+        r = subprocess.run([cli, "clip.yuv", str(W), str(H), str(qp)], cwd=str(work), env=env, capture_output=True)
+        assert r.returncode == 0
+        assert subprocess.run([cli, "--quit", sock]).returncode == 0
+        assert srv.wait(timeout=30) == 0
+    finally:
+        if srv.poll() is None:
+            srv.kill()
 
 
 def test_missing_checkpoint_is_an_io_error(eb, tmp_path):

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(eb):
     assert len(names) >= 19
     for n in names:
         assert hasattr(lib, n), "library lacks %s declared in include/ethcnn.h" % n
-    assert lib.ethcnn_abi_version() == 2
+    assert lib.ethcnn_abi_version() == 3
 
 
 def test_missing_library_fails_loudly(eb, monkeypatch, tmp_path):
@@ -175,3 +175,45 @@ def test_python_drop_in_script_has_no_arithmetic():
     assert "numpy" not in src and "oracle" not in src
     for f in ("binding.py", "__init__.py", "net_CNN.py", "sharding.py"):
         assert "oracle" not in open(os.path.join(ROOT, "hevc-complexity-reduction_b200", f)).read().replace("oracle/", "")
+
+
+def test_server_client_protocol_against_a_fake_server(eb, tmp_path):
+    """ethcnn_request (the C client of the resident server, csrc/serve.cpp) against a Python stand-in that speaks the
+    protocol: the request line carries the client's cwd and the arguments, a "0" reply is success, an error reply
+    surfaces code and message, and a missing server is reported as such (the drop-in then works in-process)."""
+    import socket
+    import threading
+
+    sock_path = str(tmp_path / "srv.sock")
+    seen = []
+
+    def fake_server(replies):
+        srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        srv.bind(sock_path)
+        srv.listen(4)
+        for reply in replies:
+            c, _ = srv.accept()
+            buf = b""
+            while not buf.endswith(b"\n"):
+                buf += c.recv(4096)
+            seen.append(buf.decode())
+            c.sendall(reply)
+            c.close()
+        srv.close()
+
+    assert eb.request(sock_path, "clip.yuv", 64, 64, 32) is False          # nobody listens
+    t = threading.Thread(target=fake_server, args=([b"0\n", b"-1\tfile size is not a whole number of frames\n"],))
+    t.start()
+    import time
+    for _ in range(200):
+        if os.path.exists(sock_path):
+            break
+        time.sleep(0.01)
+    assert eb.request(sock_path, "clip.yuv", 1920, 1080, 27, "cu_depth.dat") is True
+    with pytest.raises(eb.EthCnnError) as ei:
+        eb.request(sock_path, "/abs/bad.yuv", 10, 10, 32, "out.dat")
+    t.join()
+    assert ei.value.code == -1 and "whole number" in str(ei.value)
+    f = seen[0].rstrip("\n").split("\t")
+    assert f[0] == "PREDICT" and f[1] == os.getcwd() and f[2:] == ["clip.yuv", "1920", "1080", "27", "cu_depth.dat"]
+    assert seen[1].split("\t")[2] == "/abs/bad.yuv"
