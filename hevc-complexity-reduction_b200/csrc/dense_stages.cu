@@ -174,19 +174,20 @@ __global__ void __launch_bounds__(192) heads_kernel(const HeadsLaunch p) {
 // GATE (AI deployment): per sub-batch  g1 = any(y64 > t1);  y32 := g1 ? y32 : 0;
 //                                      g2 = any(y32_gated > t2);  y16 := g2 ? y16 : 0.
 // When g1 is false the gated y32 is all zeros, so g2 = (0 > t2).
-__global__ void gate_kernel(float* __restrict__ prob, const unsigned* __restrict__ flags, float t2, long long n_total,
-                            int ctus_per_frame, int chunks_per_frame) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // one thread per (CTU, slot 1..20)
-  if (i >= n_total * 20) return;
-  const long long n = i / 20;
-  const int slot = 1 + int(i - n * 20);
-  const long long f = n / ctus_per_frame;
-  const int r = int(n - f * ctus_per_frame);
-  const unsigned fl = flags[f * chunks_per_frame + r / kSubBatch];
+__global__ void gate_kernel(float* __restrict__ prob, const unsigned* __restrict__ flags, float t2, int ctus_per_frame,
+                            int chunks_per_frame) {
+  // one block per (frame, sub-batch); almost always both gates are open and the block has nothing to do
+  const int f = blockIdx.x / chunks_per_frame, ch = blockIdx.x - f * chunks_per_frame;
+  const unsigned fl = flags[blockIdx.x];
   const bool g1 = (fl & 1u) != 0;
   const bool g2 = g1 ? ((fl & 2u) != 0) : (0.0f > t2);
-  const bool keep = (slot < 5) ? g1 : g2;
-  if (!keep) prob[n * kProbs + slot] = 0.0f;
+  if (g1 && g2) return;
+  const int r0 = ch * kSubBatch, rows = min(kSubBatch, ctus_per_frame - r0);
+  float* base = prob + (size_t(f) * ctus_per_frame + r0) * kProbs;
+  for (int i = threadIdx.x; i < rows * 20; i += blockDim.x) {
+    const int n = i / 20, slot = 1 + i - n * 20;
+    if (!((slot < 5) ? g1 : g2)) base[n * kProbs + slot] = 0.0f;
+  }
 }
 
 // GATE + EXPORT: the same rule, reading the raw probabilities from a library-owned staging buffer and writing the final
@@ -250,8 +251,8 @@ cudaError_t launch_heads(const HeadsLaunch& p, cudaStream_t stream) {
 cudaError_t launch_gate(float* prob, const unsigned* flags, float t2, long long n_total, int ctus_per_frame,
                         int chunks_per_frame, cudaStream_t stream) {
   if (n_total <= 0) return cudaSuccess;
-  const long long work = n_total * 20;
-  gate_kernel<<<unsigned((work + 255) / 256), 256, 0, stream>>>(prob, flags, t2, n_total, ctus_per_frame, chunks_per_frame);
+  const long long n_frames = n_total / ctus_per_frame;   // a call always covers whole frames
+  gate_kernel<<<unsigned(n_frames * chunks_per_frame), 256, 0, stream>>>(prob, flags, t2, ctus_per_frame, chunks_per_frame);
   return cudaGetLastError();
 }
 
