@@ -71,6 +71,7 @@ def load_library() -> C.CDLL:
         "ethcnn_alloc_pinned": (vp, [sz]),
         "ethcnn_free_pinned": (None, [vp]),
         "ethcnn_debug_pack_model": (i32, [cp, C.c_float, vp, vp, vp, vp, vp, vp, vp]),
+        "ethcnn_debug_pack_conv_tc": (i32, [cp, C.c_float, vp]),
         "ethcnn_debug_read_thresholds": (i32, [cp, vp]),
         "ethcnn_debug_f32_to_f16": (C.c_uint16, [C.c_float]),
         "ethcnn_debug_read_scratch": (i32, [vp, i32, sz, vp]),

@@ -1337,6 +1337,18 @@ int ethcnn_debug_pack_model(const char* ckpt_prefix, float input_bound, float* c
   return ETHCNN_OK;
 }
 
+int ethcnn_debug_pack_conv_tc(const char* ckpt_prefix, float input_bound, uint8_t* blob) {
+  if (!ckpt_prefix || !blob) return fail(ETHCNN_E_ARG, "NULL argument");
+  std::map<std::string, BundleTensor> tensors;
+  std::string err;
+  if (!read_tf_bundle(ckpt_prefix, &tensors, &err))
+    return fail(err.find("cannot open") != std::string::npos ? ETHCNN_E_IO : ETHCNN_E_FORMAT, err);
+  PackedModel pm;
+  if (!pack_model(tensors, input_bound, &pm, &err)) return fail(ETHCNN_E_FORMAT, err);
+  memcpy(blob, pm.conv_tc.data(), pm.conv_tc.size());
+  return ETHCNN_OK;
+}
+
 int ethcnn_debug_read_thresholds(const char* thr_path, float thr[2]) {
   if (!thr_path || !thr) return fail(ETHCNN_E_ARG, "NULL argument");
   return read_thresholds(thr_path, &thr[0], &thr[1]);

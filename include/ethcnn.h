@@ -209,6 +209,10 @@ void ethcnn_free_pinned(void* p);
  * Any output pointer may be NULL. */
 int ethcnn_debug_pack_model(const char* ckpt_prefix, float input_bound, float* conv, float* w1, float* b1,
                             uint16_t* w1_hi, uint16_t* w1_lo, int exps[16], float* feat_bound);
+/* The conv filters as the tcgen05 conv stage consumes them (csrc/conv_tc.h): 3 branches (S, M, L) x 29696 bytes of
+ * 128-byte-swizzled K-major fp16 hi / lo tiles + the pre-scaled bias tables. */
+#define ETHCNN_CONV_TC_BLOB_BYTES (3 * 29696)
+int ethcnn_debug_pack_conv_tc(const char* ckpt_prefix, float input_bound, uint8_t* blob);
 int ethcnn_debug_read_thresholds(const char* thr_path, float thr[2]);
 uint16_t ethcnn_debug_f32_to_f16(float v);
 /* Device-side testing hook: copy back intermediates of the LAST chunk processed on device 0.

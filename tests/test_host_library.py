@@ -96,6 +96,59 @@ def test_cpp_reader_and_packer_match_oracle(eb, tmp_path, which):
     assert fbound * 2.0 ** exps[0] <= 32768.0
 
 
+def test_conv_tc_weight_image_matches_the_fragment_packing(eb, tmp_path):
+    """The tcgen05 conv stage reads the SAME hi / lo filter values as the mma.sync stage, re-arranged as 128-byte-swizzled
+    K-major UMMA tiles (csrc/conv_tc.h): element (n, k) of a [..][64] tile sits at
+    (n / 8) * 1024 + (n % 8) * 128 + ((k / 8) ^ (n % 8)) * 16 + (k % 8) * 2.  Decode every tile and compare with the scaled
+    weights' fp16 split; the tables hold the biases pre-scaled by the same powers of two."""
+    w = eo.random_weights(21)
+    prefix = str(tmp_path / "m.dat")
+    tf_bundle.write_bundle(prefix, w)
+    rc, conv, _w1, _b1, _hi, _lo, exps, _fb = _pack(eb, prefix)
+    assert rc == 0
+    lib = eb.load_library()
+    blob = np.zeros(3 * 29696, np.uint8)
+    assert lib.ethcnn_debug_pack_conv_tc(prefix.encode(), np.float32(1.0), blob.ctypes.data) == 0
+
+    def tile(raw, rows):   # -> [rows][64] uint16
+        out = np.zeros((rows, 64), np.uint16)
+        u16 = raw.view(np.uint16)
+        for n in range(rows):
+            for k in range(64):
+                out[n, k] = u16[((n >> 3) * 1024 + (n & 7) * 128 + (((k >> 3) ^ (n & 7)) << 4) + (k & 7) * 2) // 2]
+        return out
+
+    def split(v):
+        h = v.astype(np.float32).astype(np.float16)
+        l = (v.astype(np.float32) - h.astype(np.float32)).astype(np.float16)
+        return h.view(np.uint16), l.view(np.uint16)
+
+    names = lambda i: "Variable" if i == 0 else "Variable_%d" % i
+    for br, base in enumerate((12, 6, 0)):
+        b = blob[br * 29696:(br + 1) * 29696]
+        e1w, ec1, e2w, e3w = (int(x) for x in exps[4 + 4 * br: 8 + 4 * br])
+        w1 = w[names(base)].reshape(16, 16) * np.float32(2.0 ** e1w)          # [tap][co]
+        w2 = w[names(base + 2)].reshape(64, 24) * np.float32(2.0 ** e2w)      # [(ky, kx, ci)][co]
+        w3 = w[names(base + 4)].reshape(96, 32) * np.float32(2.0 ** e3w)
+        h, l = split(w1.T)
+        assert np.array_equal(tile(b[0:2048], 16)[:, :16], h) and np.array_equal(tile(b[2048:4096], 16)[:, :16], l)
+        assert not tile(b[0:2048], 16)[:, 16:].any()
+        h, l = split(w2.T)
+        t_hi, t_lo = tile(b[4096:8192], 32), tile(b[8192:12288], 32)
+        assert np.array_equal(t_hi[:24], h) and np.array_equal(t_lo[:24], l) and not t_hi[24:].any()
+        h, l = split(w3.T)
+        for t in range(2):
+            kk = slice(64 * t, min(96, 64 * t + 64))
+            n_k = kk.stop - kk.start
+            assert np.array_equal(tile(b[12288 + 4096 * t:12288 + 4096 * (t + 1)], 32)[:, :n_k], h[:, kk])
+            assert np.array_equal(tile(b[20480 + 4096 * t:20480 + 4096 * (t + 1)], 32)[:, :n_k], l[:, kk])
+        tab = b[28672:28672 + 88 * 4].view(np.float32)
+        fs = np.float32(2.0 ** int(exps[0]))
+        assert np.array_equal(tab[0:16], w[names(base + 1)] * np.float32(2.0 ** ec1))
+        assert np.array_equal(tab[16:32], conv[br][4960:4976].view(np.float32))          # the tap sums of the fragment block
+        assert np.array_equal(tab[32:56], w[names(base + 3)] * fs) and np.array_equal(tab[56:88], w[names(base + 5)] * fs)
+
+
 def test_cpp_reader_rejects_corruption(eb, tmp_path):
     w = eo.random_weights(5)
     prefix = str(tmp_path / "m.dat")
