@@ -43,7 +43,7 @@ bool fill_addr(const char* path, sockaddr_un* addr) {
 bool write_all(int fd, const std::string& s) {
   size_t done = 0;
   while (done < s.size()) {
-    const ssize_t n = write(fd, s.data() + done, s.size() - done);
+    const ssize_t n = send(fd, s.data() + done, s.size() - done, MSG_NOSIGNAL);   // a vanished peer must not kill the server
     if (n <= 0) {
       if (n < 0 && errno == EINTR) continue;
       return false;
