@@ -65,6 +65,10 @@ __device__ __forceinline__ float2 lds_f32x2(uint32_t addr) {
 
 // D(16x8, fp32) += A(16x16, fp16) * B(16x8, fp16); fragment layouts as in the PTX ISA.
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], const uint2 b) {
+#ifdef ETHCNN_EXP_NO_HMMA   // measurement only: the SIMT skeleton without the tensor instructions
+  d[0] += __uint_as_float(a[0] ^ b.x), d[1] += __uint_as_float(a[1]), d[2] += __uint_as_float(a[2] ^ b.y), d[3] += __uint_as_float(a[3]);
+  return;
+#endif
   asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
@@ -103,6 +107,10 @@ __device__ __forceinline__ float2 sub2(float2 a, float2 b) {
 
 // One accumulator pair -> leaky(d * u + b) -> packed fp16 hi pair and lo pair with hi + lo == value to ~22 bits.
 __device__ __forceinline__ void act_split(float d0, float d1, float2 u, float2 b, uint32_t& hi, uint32_t& lo) {
+#ifdef ETHCNN_EXP_NO_ACT    // measurement only: the MMA skeleton without the fragment epilogues
+  hi = __float_as_uint(d0 + u.x), lo = __float_as_uint(d1 + b.x);
+  return;
+#endif
   const float2 t = fma2(make_float2(d0, d1), u, b);
   const float2 m = mul2(t, make_float2(0.2f, 0.2f));
   const float2 r = make_float2(fmaxf(m.x, t.x), fmaxf(m.y, t.y));   // Maximum(alpha*x, x)
@@ -111,6 +119,14 @@ __device__ __forceinline__ void act_split(float d0, float d1, float2 u, float2 b
   const __half2 lh = __floats2half2_rn(l.x, l.y);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&lh);
+}
+
+// two fp16 features -> global memory
+__device__ __forceinline__ void stg32(__half* p, uint32_t v) {
+#ifdef ETHCNN_EXP_NO_STG    // measurement only: (almost) no feature stores
+  if (v != 0x7fff7fffu) return;
+#endif
+  *reinterpret_cast<uint32_t*>(p) = v;
 }
 
 __device__ __forceinline__ uint32_t centred_half2(uint32_t biased_bits, float centre) {
@@ -181,6 +197,21 @@ __device__ __forceinline__ void load_x(int pool, uint32_t blk, int T, int d, uin
   }
 }
 
+#ifdef ETHCNN_EXP_TIMING   // measurement only: cycles per phase of the warp tasks (per-warp counters in shared memory, folded at exit)
+__device__ unsigned long long g_conv_phase[3][8];
+__shared__ unsigned int s_conv_phase[16][24];
+#define PH_BEGIN() long long ph_t = clock64()
+#define PH_MARK(br, k)                                                                     \
+  do {                                                                                     \
+    const long long ph_n = clock64();                                                      \
+    if ((threadIdx.x & 31) == 0) s_conv_phase[threadIdx.x >> 5][(br) * 8 + (k)] += (unsigned int)(ph_n - ph_t); \
+    ph_t = ph_n;                                                                           \
+  } while (0)
+#else
+#define PH_BEGIN()
+#define PH_MARK(br, k)
+#endif
+
 struct QuadSet {        // what a lane needs to know about its quad in set A or B
   uint32_t blk;         // shared-memory address of the quad's pixel block inside its CTU tile
   uint32_t wsum;        // shared-memory address of this lane's share of the quad's window sum (block-sum table)
@@ -196,6 +227,9 @@ struct QuadSet {        // what a lane needs to know about its quad in set A or 
 __device__ __forceinline__ void warp_task(const int pool, const uint32_t wb, const float cst, const float fscale, const int lane,
                                        const QuadSet qa, const QuadSet qb, const int g24) {
   const int d = lane & 3;
+  const int phb = pool == 1 ? 0 : (pool == 2 ? 1 : 2);
+  (void)phb;
+  PH_BEGIN();
   // leaky(v) * 2^e == leaky(v * 2^e): the power-of-two operand scales are folded into the unscale factors and biases
   const float sc1 = lds_f32(wb + 4 * (kHdrOff + 3));
   const float u1 = lds_f32(wb + 4 * kHdrOff) * cst * sc1;     // per unit of sum((256 s - W) / 32 * B)
@@ -248,8 +282,10 @@ __device__ __forceinline__ void warp_task(const int pool, const uint32_t wb, con
       if (st) bb_lo = lo2, bb_hi = hi2; else ba_lo = lo2, ba_hi = hi2;
     }
     const float2 be_lo = st ? bb_lo : ba_lo, be_hi = st ? bb_hi : ba_hi;
+    PH_MARK(phb, 0);   // task set-up / window sums
     uint32_t xh[16];
     load_x(pool, blk, T, d, xh);
+    PH_MARK(phb, 1);   // pixel loads + conversion
     float d2[3][4];
 #pragma unroll
     for (int nt = 0; nt < 3; ++nt) d2[nt][0] = d2[nt][1] = d2[nt][2] = d2[nt][3] = 0.f;
@@ -277,6 +313,7 @@ __device__ __forceinline__ void warp_task(const int pool, const uint32_t wb, con
         mma3(d2[nt], a2h, a2l, wh, wl);
       }
     }
+    PH_MARK(phb, 2);   // conv1 + epilogue + conv2 MMAs
     // conv2 outputs of regions 2T (c0, c1) and 2T+1 (c2, c3): features (already scaled by 2^feat_exp, hi/lo)
     uint32_t cur_h[6], cur_l[6];   // pair index 3 (r - 2T) + nt
 #pragma unroll
@@ -285,11 +322,12 @@ __device__ __forceinline__ void warp_task(const int pool, const uint32_t wb, con
       act_split(d2[nt][0], d2[nt][1], u2, b2, cur_h[nt], cur_l[nt]);
       act_split(d2[nt][2], d2[nt][3], u2, b2, cur_h[3 + nt], cur_l[3 + nt]);
       const int o = c2_off + T * g24 + 8 * nt + 2 * d;
-      *reinterpret_cast<uint32_t*>(hi + o) = cur_h[nt];
-      *reinterpret_cast<uint32_t*>(lo + o) = cur_l[nt];
-      *reinterpret_cast<uint32_t*>(hi + o + 24) = cur_h[3 + nt];
-      *reinterpret_cast<uint32_t*>(lo + o + 24) = cur_l[3 + nt];
+      stg32(hi + o, cur_h[nt]);
+      stg32(lo + o, cur_l[nt]);
+      stg32(hi + o + 24, cur_h[3 + nt]);
+      stg32(lo + o + 24, cur_l[3 + nt]);
     }
+    PH_MARK(phb, 3);   // conv2 epilogue + feature stores
     if (st == 0) {
 #pragma unroll
       for (int i = 0; i < 6; ++i) keep_h[i] = cur_h[i], keep_l[i] = cur_l[i];
@@ -307,6 +345,7 @@ __device__ __forceinline__ void warp_task(const int pool, const uint32_t wb, con
           mma3(d3[nt], a3h, a3l, wh, wl);
         }
       }
+      PH_MARK(phb, 4);   // conv3 MMAs
     }
   }
 
@@ -316,11 +355,12 @@ __device__ __forceinline__ void warp_task(const int pool, const uint32_t wb, con
     uint32_t h0, l0, h1, l1;
     act_split(d3[nt][0], d3[nt][1], u3, b3, h0, l0);
     act_split(d3[nt][2], d3[nt][3], u3, b3, h1, l1);
-    *reinterpret_cast<uint32_t*>(qa.hi + qa.c3_off + 8 * nt + 2 * d) = h0;
-    *reinterpret_cast<uint32_t*>(qa.lo + qa.c3_off + 8 * nt + 2 * d) = l0;
-    *reinterpret_cast<uint32_t*>(qb.hi + qb.c3_off + 8 * nt + 2 * d) = h1;
-    *reinterpret_cast<uint32_t*>(qb.lo + qb.c3_off + 8 * nt + 2 * d) = l1;
+    stg32(qa.hi + qa.c3_off + 8 * nt + 2 * d, h0);
+    stg32(qa.lo + qa.c3_off + 8 * nt + 2 * d, l0);
+    stg32(qb.hi + qb.c3_off + 8 * nt + 2 * d, h1);
+    stg32(qb.lo + qb.c3_off + 8 * nt + 2 * d, l1);
   }
+  PH_MARK(phb, 5);     // conv3 epilogue + stores
 }
 
 constexpr int kTileBytes = kCtu * kCtu;                       // 4096
@@ -342,6 +382,9 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
   uint64_t* ready = empty + kConvStages;                                          // block sums of the group tabulated
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef ETHCNN_EXP_TIMING
+  if (lane < 24) s_conv_phase[warp][lane] = 0;
+#endif
   {
     const float4* src = reinterpret_cast<const float4*>(p.convw);
     float4* dst = reinterpret_cast<float4*>(wsm);
@@ -433,8 +476,14 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
       if (grp >= n_groups) break;
       const int stage = j % kConvStages;
       const uint32_t parity = (j / kConvStages) & 1;
+#ifdef ETHCNN_EXP_TIMING
+      const long long w0 = clock64();
+#endif
       mbar_wait(&full[stage], parity);
       mbar_wait(&ready[stage], parity);
+#ifdef ETHCNN_EXP_TIMING
+      if (lane == 0) s_conv_phase[warp][6] += (unsigned int)(clock64() - w0);
+#endif
       const uint32_t tile0 = smem_u32(tiles + stage * kStageBytes);
       const uint32_t sum0 = smem_u32(sums + stage * kSumWords);
       const int d = lane & 3;
@@ -477,10 +526,25 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[stage]);
     }
+#ifdef ETHCNN_EXP_TIMING
+    __syncwarp();
+    if (lane < 24 && s_conv_phase[warp][lane]) atomicAdd(&g_conv_phase[lane >> 3][lane & 7], (unsigned long long)s_conv_phase[warp][lane]);
+#endif
   }
 }
 
 }  // namespace
+
+#ifdef ETHCNN_EXP_TIMING
+}  // namespace ethcnn
+extern "C" int ethcnn_debug_conv_phases(unsigned long long* out24, int reset) {
+  unsigned long long z[24] = {};
+  if (cudaMemcpyFromSymbol(out24, ethcnn::g_conv_phase, sizeof(z)) != cudaSuccess) return -1;
+  if (reset && cudaMemcpyToSymbol(ethcnn::g_conv_phase, z, sizeof(z)) != cudaSuccess) return -1;
+  return 0;
+}
+namespace ethcnn {
+#endif
 
 cudaError_t conv_features_configure() {
   cudaError_t e = cudaFuncSetAttribute(conv_features_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes);

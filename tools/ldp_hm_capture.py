@@ -20,7 +20,7 @@ sys.path.insert(0, ROOT)
 from oracle import assets  # noqa: E402
 from oracle import ethcnn_oracle as eo  # noqa: E402
 
-LDP_BIN = "/root/reference/HM-16.5_Test_LDP/bin"
+LDP_BIN, _WHY = assets.hm_dir("LDP")   # None unless running the prebuilt encoder was opted into (oracle/assets.py)
 W, H, NF, QP = 416, 240, 5, 32
 
 
@@ -38,6 +38,8 @@ def clip():
 
 def run_hm_ldp(work, answer):
     """Run the encoder in `work`; `answer(i_frame, w, h, qp, resi_luma) -> (prob, state)` is called per P frame."""
+    if LDP_BIN is None:
+        raise RuntimeError(_WHY)
     os.makedirs(work, exist_ok=True)
     hm = os.path.join(work, "TAppEncoderStatic")
     shutil.copyfile(os.path.join(LDP_BIN, "TAppEncoderStatic"), hm)
