@@ -1,22 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- CTUs/sec of the ETH-CNN CU-partition predictor (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|4|5] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (config.workload): BASELINE config 2 -- synthetic 1920x1080 8-bit 4:2:0, 50 frames per rank,
-QP cycling over {22, 27, 32, 37} step by step (one deployed checkpoint per QP range).  One "step" = one
-pass of the hot path over one 50-frame clip per rank (25 500 CTUs per rank).  With N ranks the sequence
-is N x 50 frames sharded in contiguous frame ranges (weak scaling) and every step ends with the NCCL
-gather of the per-rank cu_depth rows to rank 0.
+One "step" = one pass of the hot path over one batch of synthetic input.  Workloads (BASELINE.json `configs`):
 
-  value  device-resident: luma already in HBM, kernels + gather, CUDA events, max over ranks
-  e2e    the public host API (ethcnn_predict_luma through ctypes) from PINNED HOST memory: H2D of the
-         luma planes, kernels, D2H of the probabilities (+ gather), every step
-  roofline       dominant kernel: algorithmic bytes (or FLOPs) of its launches / its CUDA-event time
-  cpu_baseline   the oracle port of the reference's script on the host cores (rank 0, N = 1, bounded)
+  config 2 (headline, default)  1920x1080, 50 frames PER RANK per step, QP cycling 22/27/32/37        weak scaling
+  config 3                      4928x3264, 50 frames, QP 32, frames split 7,7,6,... over the ranks     strong scaling
+  config 4                      2880x1920, 425 frames, QP 27, split 107,106,...; also looped >= 2 s    strong scaling
+  config 5                      1920x1080 residue stream, 240 frames, QP 37, LDP residual-CNN weights  strong scaling
 
---impl reference times that CPU port alone (the reference's TensorFlow cannot be installed here).
+The JSON line describes `--config` (default 2); without `--config` the other three are measured briefly as well and
+reported under "other_configs", and configs 2 and 4 are additionally looped back to back for >= 2 s ("sustained").
+
+  value     device-resident: luma already in HBM, kernels + gather, CUDA events on the launching stream, max over ranks
+  e2e       the public host API (ethcnn_predict_luma through ctypes) from PINNED HOST memory: H2D of the luma planes,
+            kernels, D2H of the probabilities (+ gather), every step
+  roofline  dominant kernel: algorithmic FLOPs (SURVEY.md section 8(d) per-CTU figures x the CTUs of a launch) / its
+            CUDA-event time, against the measured bf16 tensor peak (burst if the timed region is < 1 s, else sustained)
+  cpu_baseline   the oracle port of the reference's script on the host cores (rank 0, N = 1, bounded sample)
+
+--impl reference times that CPU port alone (the reference's TensorFlow cannot be installed here), same workload string.
+The product arm never imports oracle/: frames and the encoder-like model directory come from tools/synth.py.
 """
 from __future__ import annotations
 
@@ -26,7 +32,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -34,48 +39,61 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H, FRAMES = 1920, 1080, 50
-QPS = (22, 27, 32, 37)
-CTUS_PER_FRAME = 30 * 17
 ALG_BYTES_PER_CTU = 4096 + 84
 ALG_FLOP_PER_CTU = 3104298              # 2 * 1 552 149 MAC
-FC1_FLOP_PER_CTU = 2 * 1204224
 CONV_FLOP_PER_CTU = 2 * 279552
-FP32_FFMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal, not measured
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch over 25 500 CTUs, from the `ncu --set full` captures
-# summarised in profiles/r01h_conv_v4.md (conv) and profiles/r01h_fc_pair.md (fused FC), per CTU
+SCRATCH_BYTES_PER_CTU = 2 * 2 * 2688    # the features as fp16 hi + lo, written by the conv kernel and read by the FC kernel
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch, per CTU, from the `ncu --set full` captures under profiles/
 NCU_DRAM_BYTES_PER_CTU = {"conv": (104.451328e6 + 223.326720e6) / 25500, "fc1": (290.425600e6 + 5.473792e6) / 25500}
 NCU_DRAM_SOURCE = {"conv": "profiles/r01h_conv_v4.md", "fc1": "profiles/r01h_fc_pair.md"}
 
+MODE_AI, MODE_LDP = 0, 1
+CONFIGS = {
+    2: dict(w=1920, h=1080, frames=50, qps=(22, 27, 32, 37), mode=MODE_AI, scaling="weak", residue=False,
+            workload="config2: 1920x1080 4:2:0, 50 frames per rank per step, QP cycling 22/27/32/37"),
+    3: dict(w=4928, h=3264, frames=50, qps=(32,), mode=MODE_AI, scaling="strong", residue=False,
+            workload="config3: 4928x3264 4:2:0, 50 frames per step sharded in contiguous frame ranges, QP 32"),
+    4: dict(w=2880, h=1920, frames=425, qps=(27,), mode=MODE_AI, scaling="strong", residue=False,
+            workload="config4: 2880x1920 4:2:0, 425 frames per step sharded in contiguous frame ranges, QP 27"),
+    5: dict(w=1920, h=1080, frames=240, qps=(37,), mode=MODE_LDP, scaling="strong", residue=True,
+            workload="config5: 1920x1080 residue stream, 240 frames per step, QP 37, LDP residual-CNN weights"),
+}
 
-def make_clip(seed0: int, n_base: int = 5) -> np.ndarray:
-    """50 luma frames [50, H, W] uint8: a few procedural frames (oracle.synth_frame) and shifted copies."""
-    from oracle import ethcnn_oracle as eo
 
-    base = [eo.synth_frame(W, H, seed0 + k) for k in range(n_base)]
-    out = np.empty((FRAMES, H, W), dtype=np.uint8)
-    for k in range(FRAMES):
-        out[k] = np.roll(base[k % n_base], shift=(8 * (k // n_base), 16 * (k // n_base)), axis=(0, 1))
+def ctus_per_frame(cfg):
+    return -(-cfg["w"] // 64) * -(-cfg["h"] // 64)
+
+
+def frame_range(n_frames, world, rank):
+    base, rem = divmod(n_frames, world)
+    return rank * base + min(rank, rem), base + (1 if rank < rem else 0)
+
+
+def rank_frames(cfg, world, rank):
+    """(first frame, frames) this rank holds per step: weak = every rank its own `frames`; strong = a contiguous range."""
+    if cfg["scaling"] == "weak":
+        return rank * cfg["frames"], cfg["frames"]
+    return frame_range(cfg["frames"], world, rank)
+
+
+def clip_frames(cfg, f0, nf, seed0):
+    """Frames [f0, f0 + nf) of the config's global synthetic sequence (deterministic, independent of the sharding)."""
+    from tools import synth
+
+    gen = synth.synth_residue_frame if cfg["residue"] else synth.synth_frame
+    nb = 5
+    base = {}
+    out = np.empty((nf, cfg["h"], cfg["w"]), np.uint8)
+    for i in range(nf):
+        k = f0 + i
+        if k % nb not in base:
+            base[k % nb] = gen(cfg["w"], cfg["h"], seed0 + k % nb)
+        out[i] = np.roll(base[k % nb], shift=(8 * (k // nb), 16 * (k // nb)), axis=(0, 1))
     return out
 
 
-def prepare_models():
-    """Directory with the four AI checkpoints (deployed ones when the box has them, synthetic otherwise)."""
-    from oracle import assets, tf_bundle
-    from oracle import ethcnn_oracle as eo
-
-    d = tempfile.mkdtemp(prefix="ethcnn_bench_")
-    present = assets.materialize(d, "AI")
-    synthetic = []
-    for qp, name in assets.AI_MODELS.items():
-        if name not in present:
-            tf_bundle.write_bundle(os.path.join(d, name), eo.random_weights(100 + qp))
-            synthetic.append(qp)
-    return d, synthetic
-
-
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while a timed region runs."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -93,6 +111,7 @@ class ClockSampler(object):
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+        return self
 
     def stop(self):
         if self.proc is None:
@@ -102,7 +121,7 @@ class ClockSampler(object):
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for line in open(self.path):
             p = [x.strip() for x in line.split(",")]
             if len(p) < 9:
@@ -110,6 +129,7 @@ class ClockSampler(object):
             try:
                 sm.append(float(p[1]))
                 mx.append(float(p[2]))
+                pw.append(float(p[3]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
@@ -118,15 +138,17 @@ class ClockSampler(object):
         os.remove(self.path)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        busy = sorted(sm)[len(sm) // 2:]  # upper half = samples under load
-        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        order = np.argsort(pw)[len(pw) // 2:]  # the half of the samples with the highest power draw = under load
+        return {"sm_mhz": float(np.median(np.array(sm)[order])), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": float(max(pw))}
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
 _POOL_W = {}
+_POOL_CFG = {}
 
 
-def _pool_init(model_dir):
+def _pool_init(model_dir, mode, qps):
     os.environ["OMP_NUM_THREADS"] = "1"
     os.environ["OPENBLAS_NUM_THREADS"] = "1"
     try:
@@ -135,31 +157,35 @@ def _pool_init(model_dir):
     except Exception:
         pass
     from oracle import assets, tf_bundle
-    for qp, name in assets.AI_MODELS.items():
+    for qp in qps:
+        name = assets.LDP_MODEL if mode == MODE_LDP else assets.AI_MODELS[min(assets.AI_MODELS, key=lambda k: abs(k - qp))]
         _POOL_W[qp] = tf_bundle.read_bundle(os.path.join(model_dir, name))
+    _POOL_CFG["mode"] = mode
 
 
 def _pool_frame(args):
     from oracle import ethcnn_oracle as eo
     luma, qp = args
-    vh, vw = -(-H // 64) * 64, -(-W // 64) * 64
-    pad = np.zeros((vh, vw), np.uint8)
-    pad[:H, :W] = luma
-    return eo.predict_frame(pad, qp, _POOL_W[qp], eo.MODE_AI, (0.5, 0.5))
+    h, w = luma.shape
+    pad = np.zeros((-(-h // 64) * 64, -(-w // 64) * 64), np.uint8)
+    pad[:h, :w] = luma
+    mode = eo.MODE_LDP if _POOL_CFG["mode"] == MODE_LDP else eo.MODE_AI
+    return eo.predict_frame(pad, qp, _POOL_W[qp], mode, (0.5, 0.5))
 
 
 class CpuReference(object):
-    """The oracle port run the reference's way (per frame: pad, slice 64x64 CTUs in raster order, sub-batches
-    of <= 1024 through the fp32 net, gates), frames farmed out to one worker process per host core."""
+    """The oracle port run the reference's way (per frame: pad, slice 64x64 CTUs in raster order, sub-batches of <= 1024
+    through the fp32 net, gates), frames farmed out to one worker process per host core.  Checker code: only the
+    cpu_baseline leg and --impl reference come here."""
 
-    def __init__(self, model_dir):
+    def __init__(self, model_dir, cfg):
         import multiprocessing as mp
         from concurrent.futures import ProcessPoolExecutor
 
         self.cores = os.cpu_count() or 1
         self.pool = ProcessPoolExecutor(max_workers=self.cores, mp_context=mp.get_context("fork"),
-                                        initializer=_pool_init, initargs=(model_dir,))
-        list(self.pool.map(_pool_frame, [(np.zeros((H, W), np.uint8), 32)] * self.cores))  # start the workers
+                                        initializer=_pool_init, initargs=(model_dir, cfg["mode"], cfg["qps"]))
+        list(self.pool.map(_pool_frame, [(np.zeros((64, 64), np.uint8), cfg["qps"][0])] * self.cores))  # start the workers
 
     def run(self, frames: np.ndarray, qp: int) -> np.ndarray:
         return np.concatenate(list(self.pool.map(_pool_frame, [(f, qp) for f in frames])), axis=0)
@@ -168,36 +194,52 @@ class CpuReference(object):
         self.pool.shutdown()
 
 
+def cpu_model_dir(cfg):
+    """Encoder-like directory for the CPU port (checker side: oracle.assets)."""
+    from oracle import assets
+
+    d = tempfile.mkdtemp(prefix="ethcnn_ref_")
+    assets.materialize(d, "LDP" if cfg["mode"] == MODE_LDP else "AI")
+    return d
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    model_dir, synthetic = prepare_models()
-    ref = CpuReference(model_dir)
-    clip = make_clip(0)
-    # bounded sample: size the per-step frame count so that steps+warmup finish in a couple of minutes
+    cfg = CONFIGS[args.config or 2]
+    from tools import synth
+
+    d = cpu_model_dir(cfg)
+    missing = [qp for qp in cfg["qps"] if cfg["mode"] == MODE_AI and not os.path.exists(os.path.join(d, synth.AI_MODELS[qp] + ".index"))]
+    for qp in missing:
+        synth.write_bundle(os.path.join(d, synth.AI_MODELS[qp]), synth.random_cnn_weights(100 + qp))
+    ref = CpuReference(d, cfg)
+    clip = clip_frames(cfg, 0, min(cfg["frames"], max(ref.cores, 8)), 0)
+    # bounded sample: size the per-step frame count so that steps + warm-up finish in a couple of minutes
     t = time.time()
-    ref.run(clip[:ref.cores], 32)
-    per_frame = (time.time() - t) / ref.cores
+    ref.run(clip[:ref.cores], cfg["qps"][0])
+    per_frame = (time.time() - t) / min(ref.cores, len(clip))
     budget = 120.0 / max(1, args.steps + args.warmup)
-    n = int(max(1, min(FRAMES, budget / max(per_frame, 1e-6))))
+    n = int(max(1, min(len(clip), budget / max(per_frame, 1e-6))))
+    nq = len(cfg["qps"])
     for i in range(args.warmup):
-        ref.run(clip[:n], QPS[i % 4])
+        ref.run(clip[:n], cfg["qps"][i % nq])
     t0 = time.time()
     for i in range(args.steps):
-        ref.run(clip[:n], QPS[i % 4])
+        ref.run(clip[:n], cfg["qps"][i % nq])
     dt = time.time() - t0
     ref.close()
-    v = args.steps * n * CTUS_PER_FRAME / dt
+    v = args.steps * n * ctus_per_frame(cfg) / dt
     line = {
         "impl": "reference", "metric": "CTUs/sec (ETH-CNN inference)", "value": v, "unit": "CTU/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "config2: 1920x1080 4:2:0, QP cycling 22/27/32/37", "frames_per_step": n,
-                   "note": "TensorFlow is not installable here: this is the oracle port of video_to_cu_depth.py/net_CNN.py "
-                           "(numpy fp32, per-frame CTU slicing, sub-batches of 1024, gates), one worker process per core"},
+        "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["workload"]},
         "cpu_baseline": {"value": v, "unit": "CTU/s", "cores": ref.cores, "kind": "port",
-                         "sample": "%d frames of 1920x1080 per step, %d steps" % (n, args.steps)},
+                         "sample": "%d frames of %dx%d per step, %d steps; TensorFlow 1.x is not installable here, this is the oracle "
+                                   "port of video_to_cu_depth.py / net_CNN.py (numpy fp32, per-frame CTU slicing, sub-batches of "
+                                   "1024, gates), one worker process per core" % (n, cfg["w"], cfg["h"], args.steps)},
         "e2e": {"value": v, "unit": "CTU/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -206,101 +248,110 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
-def run_ours(args):
+class Ctx(object):
+    pass
+
+
+def pin_rank_to_cores(local, n_local):
+    """Give every rank of the node its own slice of the host cores (the H2D staging and the launch thread stay put)."""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        per = len(cpus) // max(1, n_local)
+        if per >= 2:
+            os.sched_setaffinity(0, set(cpus[local * per:(local + 1) * per]))
+            return per
+    except Exception:
+        pass
+    return 0
+
+
+def measure_config(cx, cfg_id, steps, warmup, want_e2e=True, want_check=True, sustain_s=0.0, h2d_probe=False):
+    """All numbers of one config at the current world size.  Returns a dict (rank 0 fills it completely)."""
     import torch
     import torch.distributed as dist
 
     import ethcnn_b200 as eb
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("--gpus %d needs torchrun (one rank per GPU)" % args.gpus)
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    model_dir, synthetic = prepare_models()
-    net = eb.EthCnn(model_dir, None, eb.MODE_AI, device=local)
-    n_ctus = FRAMES * CTUS_PER_FRAME
-
-    # one clip per QP (4 x 103.7 MB of luma > 126 MB L2, so a step never finds its input in L2)
+    cfg = CONFIGS[cfg_id]
+    world, rank, dev, stream = cx.world, cx.rank, cx.dev, cx.stream
+    net = cx.nets[cfg["mode"]]
+    W, H, cpf = cfg["w"], cfg["h"], ctus_per_frame(cfg)
+    f0, nf = rank_frames(cfg, world, rank)
+    total_frames = cfg["frames"] * world if cfg["scaling"] == "weak" else cfg["frames"]
+    n_ctus = nf * cpf                 # this rank, per step
+    total_ctus = total_frames * cpf   # the job, per step
+    qps = cfg["qps"]
+    nq = len(qps)
+    # one clip per QP for the weak config (4 x 103.7 MB of luma > 126 MB L2, so a step never finds its input in L2);
+    # the strong configs hold one sequence that is itself several times the L2
+    n_clips = nq if cfg["scaling"] == "weak" else 1
     clips_host, clips_dev = [], []
-    for i, qp in enumerate(QPS):
-        c = torch.from_numpy(make_clip(1000 * rank + 10 * i)).pin_memory()
+    for i in range(n_clips):
+        seed0 = (1000 * rank + 10 * i) if cfg["scaling"] == "weak" else 7000 * cfg_id
+        c = torch.from_numpy(clip_frames(cfg, 0 if cfg["scaling"] == "weak" else f0, nf, seed0))
+        c = c.pin_memory() if (want_e2e or h2d_probe) else c
         clips_host.append(c)
         clips_dev.append(c.to(dev))
-    out_dev = torch.empty((n_ctus, 21), dtype=torch.float32, device=dev)
-    out_host = torch.empty((n_ctus, 21), dtype=torch.float32).pin_memory()
-    gather_buf = [torch.empty_like(out_dev) for _ in range(world)] if (world > 1 and rank == 0) else None
-    stream = torch.cuda.current_stream()
-    # N > 1: the per-rank rows reach rank 0 through a gather buffer in PEER memory (the gate kernel's stores cross
-    # NVLink; no collective on the data path).  If the devices cannot map each other: NCCL gather after the kernels.
-    peer = None
-    if world > 1 and not args.nccl_gather:
-        peer = eb.sharding.PeerGather(net, world * n_ctus, 21, dst=0, device=dev)
+    out_dev = torch.empty((max(1, n_ctus), 21), dtype=torch.float32, device=dev)
+    out_host = torch.empty((max(1, n_ctus), 21), dtype=torch.float32).pin_memory()
+    first_row = f0 * cpf
+
+    peer = host_rows = None
+    if world > 1 and not cx.args.nccl_gather:
+        peer = eb.sharding.PeerGather(net, total_ctus, 21, dst=0, device=dev)
         if not peer.ok:
             if rank == 0:
                 print("[bench] peer gather buffer unavailable (%s): NCCL gather instead" % peer.error, file=sys.stderr)
             peer = None
-    peer_out = peer.row_ptr(rank * n_ctus) if peer is not None else 0
-    # e2e at N > 1: every rank's D2H lands in ONE page-locked shared host block at its row offset, so rank 0 owns the
-    # whole sequence's rows in host memory without a gather (falls back to H2D + NCCL gather + D2H if it cannot register)
-    host_rows = None
-    if world > 1 and not args.nccl_gather:
-        host_rows = eb.sharding.SharedHostRows(world * n_ctus, 21, dst=0)
-        ok = torch.tensor([1 if host_rows.registered else 0], dtype=torch.int32, device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if int(ok.item()) == 0:
-            host_rows.close()
-            host_rows = None
-    host_out = host_rows.row_ptr(rank * n_ctus) if host_rows is not None else 0
+        if want_e2e:
+            host_rows = eb.sharding.SharedHostRows(total_ctus, 21, dst=0)
+            ok = torch.tensor([1 if host_rows.registered else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                host_rows.close()
+                host_rows = None
+    peer_out = peer.row_ptr(first_row) if peer is not None else 0
+    host_out = host_rows.row_ptr(first_row) if host_rows is not None else 0
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def gather_nccl():
+        return eb.sharding.gather_rows(out_dev[:n_ctus], total_frames, cpf, 21, dst=0)
+
     def step_device(i):
-        k = i % 4
-        if peer is not None:   # rows land in rank 0's buffer as the kernels store them
-            net.predict_luma_device(clips_dev[k].data_ptr(), W, H, W, W * H, FRAMES, QPS[k], peer_out, stream.cuda_stream)
+        k = i % nq
+        c = clips_dev[k % n_clips]
+        if nf == 0:
             return
-        net.predict_luma_device(clips_dev[k].data_ptr(), W, H, W, W * H, FRAMES, QPS[k], out_dev.data_ptr(), stream.cuda_stream)
-        if world > 1:
-            dist.gather(out_dev, gather_buf, dst=0)
+        net.predict_luma_device(c.data_ptr(), W, H, W, W * H, nf, qps[k], peer_out if peer is not None else out_dev.data_ptr(),
+                                stream.cuda_stream)
+        if world > 1 and peer is None:
+            gather_nccl()
 
     def step_e2e(i):
-        k = i % 4
-        if host_rows is not None:   # the call's own D2H is the gather
-            net.predict_luma_ptr(clips_host[k].data_ptr(), W, H, W * H, FRAMES, QPS[k], host_out)
-            return
-        net.predict_luma_ptr(clips_host[k].data_ptr(), W, H, W * H, FRAMES, QPS[k], out_host.data_ptr())
-        if world > 1:
+        k = i % nq
+        c = clips_host[k % n_clips]
+        if nf:
+            net.predict_luma_ptr(c.data_ptr(), W, H, W * H, nf, qps[k], host_out if host_rows is not None else out_host.data_ptr())
+        if world > 1 and host_rows is None:
             out_dev.copy_(out_host, non_blocking=True)
-            dist.gather(out_dev, gather_buf, dst=0)
+            g = gather_nccl()
             if rank == 0:
-                torch.cat(gather_buf).cpu()
+                g.cpu()
 
-    def timed(step_fn, steps, warmup):
-        for i in range(warmup):
-            step_fn(i)
+    def timed(step_fn, n_steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(stream)
-        for i in range(steps):
+        for i in range(n_steps):
             step_fn(i)
         e1.record(stream)
         barrier()
-        wall_ms = (time.perf_counter() - t0) * 1e3
-        dev_ms = e0.elapsed_time(e1)
-        return dev_ms, wall_ms
+        return e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3
 
     def max_over_ranks(x):
         if world == 1:
@@ -316,28 +367,19 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    # ---- device-resident (kernel) number, with per-stage events
-    if peer is not None:
-        net.set_option(eb.OPT_STAGED_OUTPUT, 1)
+    res = {"workload": cfg["workload"], "scaling": cfg["scaling"], "ctus_per_step": total_ctus, "frames_of_rank0": nf if rank == 0 else None}
+    net.set_option(eb.OPT_STAGED_OUTPUT, 1 if peer is not None else 0)
+    # set-up, not steps: touch every QP range once so that its checkpoint is parsed, packed and resident
+    for k in range(nq):
+        step_device(k)
+    for i in range(warmup):
+        step_device(i)
+    barrier()
     net.profile_enable(True)
     for s in range(4):
         net.profile_read(s, reset=True)
-    sampler = ClockSampler(local)
-    sampler.start()   # sampled from the warm-up to the end of the e2e region (both timed regions are under load)
     launches0 = net.kernel_launches
-    # set-up, not steps: touch every QP range once so that all four checkpoints are parsed, packed and resident (a step
-    # cycles through the QPs; with W = 3 the fourth checkpoint would otherwise be loaded inside the timed region)
-    for k in range(len(QPS)):
-        step_device(k)
-    barrier()
-    # warm-up outside the profile window
-    for i in range(args.warmup):
-        step_device(i)
-    barrier()
-    for s in range(4):
-        net.profile_read(s, reset=True)
-    launches0 = net.kernel_launches
-    dev_ms, _ = timed(step_device, args.steps, 0)
+    dev_ms, _ = timed(step_device, steps)
     launches = net.kernel_launches - launches0
     stage = {}
     for s, name in enumerate(eb.STAGE_NAMES):
@@ -345,41 +387,200 @@ def run_ours(args):
         stage[name] = {"ms_total": ms, "launches": n}
     net.profile_enable(False)
     dev_ms = max_over_ranks(dev_ms)
-    value = world * args.steps * n_ctus / (dev_ms * 1e-3)
-    gather_check = None
-    if peer is not None:
-        # outside the timed regions: the rows in rank 0's peer buffer must equal an NCCL gather of the same step
+    res["value"] = steps * total_ctus / (dev_ms * 1e-3)
+    res["ms_per_step"] = dev_ms / steps
+    res["timed_region_s"] = dev_ms * 1e-3
+    res["gpu_launches"] = int(sum_over_ranks(launches))
+    res["stages"] = {name: {"ms_per_step": v["ms_total"] / steps, "launches_per_step": v["launches"] / steps} for name, v in stage.items()}
+    res["_stage_raw"] = stage
+
+    # ---- sustained: the same device-resident step looped back to back for >= sustain_s seconds, clocks sampled meanwhile
+    if sustain_s > 0:
+        n_loop = max(steps, int(np.ceil(sustain_s * 1e3 / max(1e-3, dev_ms / steps))))
+        sampler = ClockSampler(cx.local).start()
+        net.profile_enable(True)
+        for s in range(4):
+            net.profile_read(s, reset=True)
+        sus_ms, _ = timed(step_device, n_loop)
+        sstage = {}
+        for s, name in enumerate(eb.STAGE_NAMES):
+            ms, n = net.profile_read(s, reset=True)
+            sstage[name] = ms / n_loop
+        net.profile_enable(False)
+        clocks = sampler.stop()
+        sus_ms = max_over_ranks(sus_ms)
+        res["sustained"] = {"value": n_loop * total_ctus / (sus_ms * 1e-3), "unit": "CTU/s", "steps": n_loop, "seconds": sus_ms * 1e-3,
+                            "ms_per_step": sus_ms / n_loop, "stage_ms_per_step": sstage, "clocks": clocks}
+
+    # ---- N-GPU == 1-GPU bytes (outside every timed region): rank 0 recomputes ALL frames of the job on its own GPU
+    if world > 1 and want_check:
         step_device(0)
-        peer.complete()
-        net.set_option(eb.OPT_STAGED_OUTPUT, 0)
-        net.predict_luma_device(clips_dev[0].data_ptr(), W, H, W, W * H, FRAMES, QPS[0], out_dev.data_ptr(), stream.cuda_stream)
-        dist.gather(out_dev, gather_buf, dst=0)
-        torch.cuda.synchronize()
+        if peer is not None:
+            peer.complete()
+            gathered = peer.rows() if rank == 0 else None
+        else:
+            gathered = gather_nccl()
+            barrier()
         if rank == 0:
-            same = bool(torch.equal(peer.rows(), torch.cat(gather_buf)))
-            gather_check = "rows in the peer buffer are bit-identical to an NCCL gather" if same else "MISMATCH against the NCCL gather"
+            net.set_option(eb.OPT_STAGED_OUTPUT, 0)
+            same, worst = True, 0.0
+            for r in range(world):
+                rf0, rnf = rank_frames(cfg, world, r)
+                if rnf == 0:
+                    continue
+                seed0 = 1000 * r if cfg["scaling"] == "weak" else 7000 * cfg_id
+                cr = torch.from_numpy(clip_frames(cfg, 0 if cfg["scaling"] == "weak" else rf0, rnf, seed0)).to(dev)
+                alone = torch.empty((rnf * cpf, 21), dtype=torch.float32, device=dev)
+                net.predict_luma_device(cr.data_ptr(), W, H, W, W * H, rnf, qps[0], alone.data_ptr(), stream.cuda_stream)
+                torch.cuda.synchronize()
+                part = gathered[rf0 * cpf:(rf0 + rnf) * cpf]
+                if not torch.equal(part, alone):
+                    same = False
+                    worst = max(worst, float((part - alone).abs().max().item()))
+                del cr, alone
+            res["gather_check"] = ("rank 0 recomputed all %d frames of the step alone on one GPU: the gathered rows are bit-identical"
+                                   % total_frames) if same else "MISMATCH against the single-GPU recomputation (max |d| %g)" % worst
+            net.set_option(eb.OPT_STAGED_OUTPUT, 1 if peer is not None else 0)
             if not same:
-                raise SystemExit("peer gather buffer differs from the NCCL gather")
+                raise SystemExit("N-GPU rows differ from the 1-GPU rows: " + res["gather_check"])
+        barrier()
 
     # ---- end to end through the host API (pinned host buffers; H2D + kernels + D2H inside the timed region)
-    # the device timeline cannot see host work, so e2e is wall clock between synchronised barriers, max over ranks
-    _, e2e_wall_ms = timed(step_e2e, args.steps, max(3, args.warmup))
-    e2e_ms = max_over_ranks(e2e_wall_ms)
-    e2e_value = world * args.steps * n_ctus / (e2e_ms * 1e-3)
-    clocks = sampler.stop()
-    e2e_check = None
+    if want_e2e:
+        net.set_option(eb.OPT_STAGED_OUTPUT, 0)
+        for i in range(max(3, warmup)):
+            step_e2e(i)
+        _, wall_ms = timed(step_e2e, steps)
+        e2e_ms = max_over_ranks(wall_ms)
+        res["e2e"] = {"value": steps * total_ctus / (e2e_ms * 1e-3), "unit": "CTU/s", "ms_per_step": e2e_ms / steps,
+                      "h2d_bytes_per_step": total_frames * W * H, "d2h_bytes_per_step": total_ctus * 84,
+                      "timing": "wall clock between device-synchronised barriers, max over ranks",
+                      "gather": (None if world == 1 else "every rank's D2H lands in one page-locked shared host block (no collective)"
+                                 if host_rows is not None else "H2D + NCCL gather + D2H on rank 0")}
+        if host_rows is not None and want_check:
+            # rank 0's shared block must hold every rank's rows of the last e2e step
+            k = (steps - 1) % nq
+            if nf:
+                net.predict_luma_device(clips_dev[k % n_clips].data_ptr(), W, H, W, W * H, nf, qps[k], out_dev.data_ptr(), stream.cuda_stream)
+            g = gather_nccl()
+            torch.cuda.synchronize()
+            if rank == 0:
+                same = bool(np.array_equal(host_rows.rows(), g.cpu().numpy()))
+                res["e2e"]["gather_check"] = "rows in the shared host block are bit-identical to an NCCL gather" if same else "MISMATCH"
+                if not same:
+                    raise SystemExit("shared host rows differ from the NCCL gather")
+        if h2d_probe and nf:
+            # what the box can deliver: every rank copies the same luma bytes from pinned memory, nothing else running
+            buf = clips_dev[0]
+            for _ in range(3):
+                buf.copy_(clips_host[0], non_blocking=True)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                buf.copy_(clips_host[0], non_blocking=True)
+            barrier()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            gbs = steps * total_frames * W * H / dt / 1e9
+            res["e2e"]["h2d_ceiling"] = {"aggregate_gb_s": gbs, "ctu_per_s": gbs * 1e9 / 4096,
+                                         "e2e_fraction_of_ceiling": res["e2e"]["value"] / (gbs * 1e9 / 4096),
+                                         "how": "bare pinned-host -> device copies of the same bytes on all ranks at once, max over ranks"}
+    if peer is not None:
+        peer.close()
     if host_rows is not None:
-        # outside the timed region: rank 0's shared block must hold every rank's rows of the last e2e step
-        k = (args.steps - 1) % 4
-        net.predict_luma_device(clips_dev[k].data_ptr(), W, H, W, W * H, FRAMES, QPS[k], out_dev.data_ptr(), stream.cuda_stream)
-        dist.gather(out_dev, gather_buf, dst=0)
-        torch.cuda.synchronize()
-        if rank == 0:
-            same = bool(np.array_equal(host_rows.rows(), torch.cat(gather_buf).cpu().numpy()))
-            e2e_check = "rows in the shared host block are bit-identical to an NCCL gather" if same else "MISMATCH"
-            if not same:
-                raise SystemExit("shared host rows differ from the NCCL gather")
-    total_launches = int(sum_over_ranks(launches))
+        host_rows.close()
+    del clips_dev, clips_host, out_dev, out_host
+    torch.cuda.empty_cache()
+    return res
+
+
+def roofline_of(res, peaks):
+    """`roofline` of the dominant kernel + the other kernel + the whole path against the HBM roofline."""
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    burst, sustained = float(peaks.get("bf16_tflops", 1590.0)), float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+    src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    long_region = res["timed_region_s"] >= 1.0
+    tf_peak = sustained if long_region else burst
+    stage = res["_stage_raw"]
+    steps_ctus = res["ctus_per_step"] * res["timed_region_s"] / (res["ms_per_step"] * 1e-3) / max(1, res.get("_world", 1))  # per rank
+    fc_s = max(1e-12, (stage["fc1"]["ms_total"] + stage["heads"]["ms_total"]) * 1e-3)
+    conv_s = max(1e-12, stage["conv"]["ms_total"] * 1e-3)
+    kern = {"conv": (CONV_FLOP_PER_CTU, conv_s), "fc1": (ALG_FLOP_PER_CTU - CONV_FLOP_PER_CTU, fc_s)}
+    dom = "conv" if conv_s >= fc_s else "fc1"
+    names = {"conv": "conv", "fc1": "fc (FC1+FC2+FC3)"}
+    out = {}
+    for key, k in (("roofline", dom), ("roofline_other_kernel", "fc1" if dom == "conv" else "conv")):
+        flop, secs = kern[k]
+        n_launch = max(1, stage[k]["launches"])
+        r = {"kernel": names[k], "bound": "tensor", "achieved": steps_ctus * flop / secs / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
+             "peak_source": "%s, %s bf16 (timed region %.3f s)" % (src, "sustained" if long_region else "burst", res["timed_region_s"]),
+             "avg_launch_ms": stage[k]["ms_total"] / n_launch,
+             "traffic": NCU_DRAM_BYTES_PER_CTU[k] * steps_ctus / n_launch,
+             "traffic_source": "dram bytes read + written per launch, scaled per CTU from " + NCU_DRAM_SOURCE[k],
+             "algorithmic_bytes_per_launch": ALG_BYTES_PER_CTU * steps_ctus / n_launch,
+             "scratch_bytes_per_launch": SCRATCH_BYTES_PER_CTU * steps_ctus / n_launch,
+             "note": "algorithmic FLOPs of the kernel (SURVEY 8(d)) / its CUDA-event time; the kernel issues ~3x these FLOPs in fp16 "
+                     "(hi*hi + hi*lo + lo*hi split passes for fp32-class accuracy); scratch = the fp16 hi/lo features exchanged "
+                     "between the two kernels through HBM, not part of the algorithmic bytes"}
+        r["frac"] = r["achieved"] / r["peak"]
+        out[key] = r
+    per_gpu = res["value"] / max(1, res.get("_world", 1))
+    out["roofline_hbm"] = {"kernel": "whole path", "bound": "hbm", "achieved": per_gpu * ALG_BYTES_PER_CTU / 1e9, "peak": hbm_peak,
+                           "unit": "GB/s", "peak_source": src, "frac": per_gpu * ALG_BYTES_PER_CTU / 1e9 / hbm_peak}
+    out["whole_path_fraction"] = {"hbm_frac": out["roofline_hbm"]["frac"], "tensor_frac": per_gpu * ALG_FLOP_PER_CTU / 1e12 / tf_peak}
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import ethcnn_b200 as eb
+    from tools import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("--gpus %d needs torchrun (one rank per GPU)" % args.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    cores_per_rank = pin_rank_to_cores(local, world) if (world > 1 and not args.no_pin) else 0
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    main_id = args.config or 2
+    todo = [main_id] + ([c for c in (3, 4, 5) if c != main_id] if (args.config is None and not args.only_main) else [])
+    cx = Ctx()
+    cx.world, cx.rank, cx.local, cx.dev, cx.args = world, rank, local, dev, args
+    cx.stream = torch.cuda.current_stream()
+    cx.nets = {}
+    model_dirs, synthetic = {}, []
+    for cid in todo:
+        mode = CONFIGS[cid]["mode"]
+        if mode not in cx.nets:
+            model_dirs[mode] = tempfile.mkdtemp(prefix="ethcnn_bench_")
+            synthetic += synth.prepare_models(model_dirs[mode], "LDP" if mode == MODE_LDP else "AI")
+            cx.nets[mode] = eb.EthCnn(model_dirs[mode], None, eb.MODE_LDP if mode == MODE_LDP else eb.MODE_AI, device=local)
+
+    sampler = ClockSampler(local).start()   # from the warm-up to the end of the headline's e2e region (both under load)
+    main = measure_config(cx, main_id, args.steps, args.warmup, want_e2e=True, want_check=True,
+                          sustain_s=0.0, h2d_probe=True)
+    clocks = sampler.stop()
+    main["_world"] = world
+    others, sustained = {}, {}
+    if args.config is None and not args.only_main:
+        sus = measure_config(cx, main_id, 5, 3, want_e2e=False, want_check=False, sustain_s=args.sustain)
+        if "sustained" in sus:
+            sustained["config%d" % main_id] = sus["sustained"]
+        for cid in todo[1:]:
+            r = measure_config(cx, cid, max(3, min(args.steps, 10)), 3, want_e2e=True, want_check=(cid == 3),
+                               sustain_s=(args.sustain if cid == 4 else 0.0))
+            r["_world"] = world
+            if "sustained" in r:
+                sustained["config%d" % cid] = r.pop("sustained")
+            others["config%d" % cid] = r
 
     if rank == 0:
         peaks = {}
@@ -387,96 +588,70 @@ def run_ours(args):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        tf_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
-        peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-        ctus_timed = args.steps * n_ctus
-        per_stage = {}
-        for name in ("conv", "fc1", "heads", "gate"):
-            ms = stage[name]["ms_total"]
-            per_stage[name] = {"ms_per_step": ms / args.steps, "launches_per_step": stage[name]["launches"] / args.steps,
-                               "share_of_kernel_time": ms / max(1e-9, sum(v["ms_total"] for v in stage.values()))}
-        fc_s = max(1e-12, (stage["fc1"]["ms_total"] + stage["heads"]["ms_total"]) * 1e-3)
-        conv_s = max(1e-12, stage["conv"]["ms_total"] * 1e-3)
-        # per-kernel algorithmic work: CONV 559 104 FLOP/CTU, dense stages 2 545 194 FLOP/CTU
-        kern = {"conv": (CONV_FLOP_PER_CTU, conv_s), "fc1": (ALG_FLOP_PER_CTU - CONV_FLOP_PER_CTU, fc_s)}
-        dom = "conv" if conv_s >= fc_s else "fc1"
-        kfeat = 2688   # features per CTU; the kernels exchange them as fp16 hi + lo (2 x 2 x 2688 B per CTU)
-        flop, secs = kern[dom]
-        roofline = {"kernel": dom if dom == "conv" else "fc (FC1+FC2+FC3)", "bound": "tensor",
-                    "achieved": ctus_timed * flop / secs / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
-                    "traffic": NCU_DRAM_BYTES_PER_CTU[dom] * ctus_timed / max(1, stage[dom]["launches"]),
-                    "traffic_source": "dram bytes read + written per launch, scaled per CTU from " + NCU_DRAM_SOURCE[dom],
-                    "algorithmic_bytes_per_launch": (4096 + 2 * 2 * kfeat if dom == "conv" else 2 * 2 * kfeat + 84)
-                                                    * ctus_timed / max(1, stage[dom]["launches"]),
-                    "peak_source": peak_src + ", sustained bf16",
-                    "avg_launch_ms": stage[dom]["ms_total"] / max(1, stage[dom]["launches"]),
-                    "note": "algorithmic FLOPs of the kernel / its CUDA-event time; the kernel issues 3x these FLOPs in fp16 "
-                            "(hi*hi + hi*lo + lo*hi split passes for fp32-class accuracy)"}
-        roofline["frac"] = roofline["achieved"] / roofline["peak"]
-        other = "fc1" if dom == "conv" else "conv"
-        flop2, secs2 = kern[other]
-        roofline_other = {"kernel": other if other == "conv" else "fc (FC1+FC2+FC3)", "bound": "tensor",
-                          "achieved": ctus_timed * flop2 / secs2 / 1e12, "peak": tf_peak, "unit": "TFLOP/s"}
-        roofline_other["frac"] = roofline_other["achieved"] / tf_peak
-        # the whole path against the HBM roofline with its algorithmic bytes (north_star: "fraction of the HBM-read roofline")
-        roofline_hbm = {"kernel": "whole path", "bound": "hbm", "achieved": value / world * ALG_BYTES_PER_CTU / 1e9, "peak": hbm_peak,
-                        "unit": "GB/s", "peak_source": peak_src}
-        roofline_hbm["frac"] = roofline_hbm["achieved"] / hbm_peak
-        whole = {"hbm_frac": roofline_hbm["frac"], "tensor_frac": value / world * ALG_FLOP_PER_CTU / 1e12 / tf_peak}
+        rl = roofline_of(main, peaks)
+        for name, r in others.items():
+            rr = roofline_of(r, peaks)
+            r["roofline"] = {k: rr["roofline"][k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "avg_launch_ms")}
+            r["roofline_hbm_frac"] = rr["roofline_hbm"]["frac"]
+            r.pop("_stage_raw"), r.pop("_world")
+        sus_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        for name, s in sustained.items():
+            cid = int(name[-1])
+            per_gpu = s["value"] / world
+            c = CONFIGS[cid]
+            ctus_rank = c["frames"] * ctus_per_frame(c) * (1.0 if c["scaling"] == "weak" else 1.0 / world)   # per rank per step
+            s["whole_path_tensor_frac_of_sustained_peak"] = per_gpu * ALG_FLOP_PER_CTU / 1e12 / sus_peak
+            s["conv_tflops"] = CONV_FLOP_PER_CTU * ctus_rank / max(1e-9, s["stage_ms_per_step"]["conv"] * 1e-3) / 1e12
+            s["conv_frac_of_sustained_peak"] = s["conv_tflops"] / sus_peak
+            s["peak"] = {"bf16_tflops_sustained": sus_peak}
 
         cpu_baseline = None
+        cfg = CONFIGS[main_id]
         if world == 1 and not args.no_cpu_baseline:
-            ref = CpuReference(model_dir)
-            clip = clips_host[2].numpy()
+            ref = CpuReference(cpu_model_dir(cfg), cfg)
+            clip = clip_frames(cfg, 0, min(cfg["frames"], 2 * ref.cores), 0)
             t = time.time()
-            ref.run(clip[:ref.cores], 32)
-            per_frame = (time.time() - t) / ref.cores
-            n = int(max(ref.cores, min(FRAMES, 15.0 / max(per_frame, 1e-6))))
+            qp_b = cfg["qps"][min(2, len(cfg["qps"]) - 1)]
+            ref.run(clip[:ref.cores], qp_b)
+            per_frame = (time.time() - t) / min(ref.cores, len(clip))
+            n = int(max(1, min(len(clip), 15.0 / max(per_frame, 1e-6))))
             t = time.time()
-            ref.run(clip[:n], 32)
+            ref.run(clip[:n], qp_b)
             dt = time.time() - t
-            cpu_baseline = {"value": n * CTUS_PER_FRAME / dt, "unit": "CTU/s", "cores": ref.cores, "kind": "port",
-                            "sample": "%d frames of 1920x1080 at QP 32 (oracle port, one worker process per core)" % n}
+            cpu_baseline = {"value": n * ctus_per_frame(cfg) / dt, "unit": "CTU/s", "cores": ref.cores, "kind": "port",
+                            "sample": "%d frames of %dx%d at QP %d (oracle port, one worker process per core)" % (n, cfg["w"], cfg["h"], qp_b)}
             ref.close()
 
+        dense = ("simt", "tcgen05 FC1 + heads kernel", "fused tcgen05 FC1+FC2+FC3",
+                 "fused tcgen05 FC1+FC2+FC3 on CTA pairs (cta_group::2)")[cx.nets[cfg["mode"]].query(3)]
         line = {
-            "metric": "CTUs/sec (ETH-CNN inference)", "value": value, "unit": "CTU/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "metric": "CTUs/sec (ETH-CNN inference)", "value": main["value"], "unit": "CTU/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": cfg["scaling"],
             "vs_baseline": None, "dtype": "f32-class (3-pass split fp16 on tensor cores, fp32 accumulate: convs mma.sync, FC tcgen05)",
-            "data": "synthetic luma; weights: %s" % ("deployed checkpoints" if not synthetic else
-                                                     "synthetic checkpoints for QP %s" % synthetic),
-            "config": {"workload": "config2: 1920x1080 4:2:0, 50 frames per rank per step, QP cycling 22/27/32/37",
-                       "ctus_per_step": world * n_ctus,
+            "data": "synthetic luma; weights: %s" % ("deployed checkpoints" if not synthetic else "synthetic checkpoints for QP %s" % synthetic),
+            "config": {"workload": cfg["workload"], "ctus_per_step": main["ctus_per_step"],
                        "sharding": ("single GPU" if world == 1 else
-                                    "contiguous frame ranges; rows stored by the gate kernel straight into rank 0's gather buffer over "
-                                    "NVLink peer memory (no collective on the data path); e2e: NCCL gather" if peer is not None else
+                                    "contiguous frame ranges; rows stored by the gate kernel straight into rank 0's gather buffer over NVLink "
+                                    "peer memory (no collective on the data path)" if not args.nccl_gather else
                                     "contiguous frame ranges, NCCL gather to rank 0"),
-                       "gather_check": gather_check,
-                       "l2": "inputs rotate over 4 clips (415 MB luma) + ~600 MB of scratch traffic per step, larger than the 126 MB L2",
-                       "dense_path": ("simt", "tcgen05 FC1 + heads kernel", "fused tcgen05 FC1+FC2+FC3",
-                                      "fused tcgen05 FC1+FC2+FC3 on CTA pairs (cta_group::2)")[net.query(3)]},
-            "e2e": {"value": e2e_value, "unit": "CTU/s", "ms_per_step": e2e_ms / args.steps,
-                    "h2d_bytes_per_step": world * FRAMES * W * H, "d2h_bytes_per_step": world * n_ctus * 84,
-                    "timing": "wall clock between device-synchronised barriers, max over ranks",
-                    "gather": (None if world == 1 else "every rank's D2H lands in one page-locked shared host block (no collective)"
-                               if host_rows is not None else "H2D + NCCL gather + D2H on rank 0"),
-                    "gather_check": e2e_check},
-            "gpu_launches": total_launches,
+                       "gather_check": main.get("gather_check"),
+                       "l2": "inputs are several times the 126 MB L2 (config 2 rotates over 4 clips = 415 MB; the others hold one sequence "
+                             "of 0.5-2.35 GB) + ~11 KB of scratch traffic per CTU",
+                       "dense_path": dense, "cores_per_rank": cores_per_rank or None},
+            "e2e": main["e2e"],
+            "gpu_launches": main["gpu_launches"],
             "clocks": clocks,
-            "roofline": roofline,
-            "roofline_other_kernel": roofline_other,
-            "roofline_hbm": roofline_hbm,
-            "whole_path_fraction": whole,
-            "stages": per_stage,
+            "roofline": rl["roofline"], "roofline_other_kernel": rl["roofline_other_kernel"], "roofline_hbm": rl["roofline_hbm"],
+            "whole_path_fraction": rl["whole_path_fraction"],
+            "stages": main["stages"],
+            "timed_region_s": main["timed_region_s"],
+            "sustained": sustained or None,
+            "other_configs": others or None,
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line))
-    if peer is not None:
-        peer.close()
-    if host_rows is not None:
-        host_rows.close()
-    net.close()
+    for net in cx.nets.values():
+        net.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -488,8 +663,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--config", type=int, default=None, choices=sorted(CONFIGS), help="BASELINE config of the JSON line (default 2, "
+                    "with the other configs measured briefly under other_configs)")
+    ap.add_argument("--only-main", action="store_true", help="skip other_configs and the sustained legs")
+    ap.add_argument("--sustain", type=float, default=2.5, help="seconds of back-to-back steps for the sustained legs")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pin", action="store_true", help="N > 1: do not give every rank its own slice of the host cores")
     ap.add_argument("--nccl-gather", action="store_true", help="N > 1: gather with NCCL after the kernels instead of peer-memory stores")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)

@@ -29,10 +29,11 @@ from .binding import (  # noqa: F401
     library_path,
     load_library,
     ctu_grid,
+    unpack_decisions,
     request,
     request_quit,
 )
-from . import video_to_cu_depth, net_CNN, sharding  # noqa: F401
+from . import video_to_cu_depth, net_CNN, sharding, evaluation  # noqa: F401
 
 __all__ = ["EthCnn", "EthCnnError", "MODE_AI", "MODE_LDP", "PROBS_PER_CTU", "FC1_WIDTH", "library_path",
-           "load_library", "ctu_grid", "video_to_cu_depth", "net_CNN", "sharding"]
+           "load_library", "ctu_grid", "video_to_cu_depth", "net_CNN", "sharding", "evaluation", "unpack_decisions"]

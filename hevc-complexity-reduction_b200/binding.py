@@ -5,6 +5,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 import os
+import sys
 from typing import Optional, Tuple
 
 import numpy as np
@@ -53,6 +54,10 @@ def load_library() -> C.CDLL:
         "ethcnn_predict_yuv_file": (i32, [vp, cp, i32, i32, i32, cp]),
         "ethcnn_predict_luma": (i32, [vp, vp, i32, i32, sz, i32, i32, vp]),
         "ethcnn_predict_luma_device": (i32, [vp, vp, i32, i32, sz, sz, i32, i32, vp, vp]),
+        "ethcnn_predict_luma_map": (i32, [vp, vp, i32, i32, sz, i32, i32, vp, vp]),
+        "ethcnn_predict_luma_device_map": (i32, [vp, vp, i32, i32, sz, sz, i32, i32, vp, vp, vp]),
+        "ethcnn_set_decision_thresholds": (i32, [vp, vp]),
+        "ethcnn_get_decision_thresholds": (i32, [vp, vp]),
         "ethcnn_export_fc1": (i32, [vp, vp, i32, i32, sz, i32, vp]),
         "ethcnn_decisions": (i32, [vp, vp, sz, vp, vp]),
         "ethcnn_ldp_step": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp]),
@@ -65,6 +70,8 @@ def load_library() -> C.CDLL:
         "ethcnn_peer_buffer_open": (i32, [vp, vp, C.POINTER(vp)]),
         "ethcnn_peer_buffer_release": (i32, [vp, vp]),
         "ethcnn_serve": (i32, [vp, cp, i32, i32]),
+        "ethcnn_predict_yuv_file_from": (i32, [vp, cp, cp, i32, i32, i32, cp]),
+        "ethcnn_reload_thresholds": (i32, [vp, cp]),
         "ethcnn_request": (i32, [cp, cp, i32, i32, i32, cp]),
         "ethcnn_request_quit": (i32, [cp]),
         "ethcnn_request_error": (cp, []),
@@ -94,6 +101,13 @@ def ctu_grid(width: int, height: int) -> Tuple[int, int]:
     return math.ceil(height / 64), math.ceil(width / 64)
 
 
+def unpack_decisions(dmap: np.ndarray) -> np.ndarray:
+    """uint64 [n] decision words -> uint8 [n, 21] (2 = split only, 0 = no split, 1 = check both), entry k from bits [2k, 2k+1]."""
+    dmap = np.ascontiguousarray(dmap, dtype=np.uint64).reshape(-1, 1)
+    shifts = (2 * np.arange(PROBS_PER_CTU, dtype=np.uint64)).reshape(1, -1)
+    return ((dmap >> shifts) & np.uint64(3)).astype(np.uint8)
+
+
 def _ptr(a: np.ndarray) -> C.c_void_p:
     return C.c_void_p(a.ctypes.data)
 
@@ -107,6 +121,9 @@ def request(socket_path: str, yuv_path: str, width: int, height: int, qp: int, o
         return True
     msg = lib.ethcnn_request_error().decode("utf-8", "replace")
     if rc == -2 and "no server" in msg:
+        return False
+    if rc == -3 and "resident handle" in msg:   # the server holds other weights than this directory's checkpoint and refused
+        sys.stderr.write("video_to_cu_depth: %s, working in-process\n" % msg)
         return False
     raise EthCnnError(rc, "server: " + msg)
 
@@ -156,6 +173,14 @@ class EthCnn(object):
         _check(self._lib.ethcnn_predict_yuv_file(self._h, os.fsencode(yuv_path), width, height, qp, os.fsencode(out_path)))
 
     # --- get_prob() for luma in host memory (video_to_cu_depth.py:75-118)
+    def predict_yuv_file_from(self, client_dir: str, yuv_path: str, width: int, height: int, qp: int, out_path: str = "cu_depth.dat") -> None:
+        """A resident handle answering like a fresh run of the reference script from `client_dir` (see include/ethcnn.h)."""
+        _check(self._lib.ethcnn_predict_yuv_file_from(self._h, os.fsencode(client_dir), os.fsencode(yuv_path), width, height, qp,
+                                                      os.fsencode(out_path)))
+
+    def reload_thresholds(self, thr_path: Optional[str] = None) -> None:
+        _check(self._lib.ethcnn_reload_thresholds(self._h, os.fsencode(thr_path) if thr_path else None))
+
     def predict_yuv_buffer(self, yuv: np.ndarray, width: int, height: int, qp: int) -> np.ndarray:
         """yuv: uint8 array holding whole 4:2:0 frames (Y, U, V planar).  Returns float32 [n_frames*nCTU, 21]."""
         yuv = np.ascontiguousarray(yuv, dtype=np.uint8).reshape(-1)
@@ -188,6 +213,33 @@ class EthCnn(object):
         """Device pointers (ints), asynchronous on `stream` (a cudaStream_t value)."""
         _check(self._lib.ethcnn_predict_luma_device(self._h, C.c_void_p(d_y), width, height, pitch, frame_stride, n_frames,
                                                     qp, C.c_void_p(d_out), C.c_void_p(stream)))
+
+    # --- decision map (include/ethcnn.h: HM's threshold rule on the device, one 64-bit word of 21 two-bit decisions per CTU)
+    def predict_luma_map(self, y: np.ndarray, width: int, height: int, n_frames: int, qp: int,
+                         frame_stride: Optional[int] = None) -> Tuple[np.ndarray, np.ndarray]:
+        """(float32 [n_frames*nCTU, 21], uint64 [n_frames*nCTU]) -- the rows of predict_luma plus the packed decisions."""
+        y = np.ascontiguousarray(y, dtype=np.uint8)
+        if frame_stride is None:
+            frame_stride = width * height
+        rows, cols = ctu_grid(width, height)
+        out = np.empty((n_frames * rows * cols, PROBS_PER_CTU), dtype=np.float32)
+        dmap = np.empty((n_frames * rows * cols,), dtype=np.uint64)
+        _check(self._lib.ethcnn_predict_luma_map(self._h, _ptr(y), width, height, frame_stride, n_frames, qp, _ptr(out), _ptr(dmap)))
+        return out, dmap
+
+    def predict_luma_device_map(self, d_y: int, width: int, height: int, pitch: int, frame_stride: int, n_frames: int, qp: int,
+                                d_out: int, d_map: int, stream: int = 0) -> None:
+        _check(self._lib.ethcnn_predict_luma_device_map(self._h, C.c_void_p(d_y), width, height, pitch, frame_stride, n_frames,
+                                                        qp, C.c_void_p(d_out), C.c_void_p(d_map), C.c_void_p(stream)))
+
+    def set_decision_thresholds(self, thr6) -> None:
+        thr = np.asarray(thr6, dtype=np.float32).reshape(6)
+        _check(self._lib.ethcnn_set_decision_thresholds(self._h, _ptr(thr)))
+
+    def get_decision_thresholds(self) -> np.ndarray:
+        thr = np.empty(6, dtype=np.float32)
+        _check(self._lib.ethcnn_get_decision_thresholds(self._h, _ptr(thr)))
+        return thr
 
     def predict_ctus(self, ctus: np.ndarray, qp: int) -> np.ndarray:
         """ctus: uint8 [n, 64, 64].  Each CTU is treated as its own 64x64 frame, i.e. its own sub-batch of one

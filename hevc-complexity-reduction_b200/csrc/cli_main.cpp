@@ -65,7 +65,11 @@ int main(int argc, char** argv) {
                std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count());
         return 0;
       }
-      if (rc != ETHCNN_E_IO || !*ethcnn_request_error() || strstr(ethcnn_request_error(), "no server") == nullptr) {
+      // two cases are not failures of this run: nobody listens, or the server holds OTHER weights than this directory's
+      // checkpoint (it refuses rather than answer with them) -- both are served in-process, like a run without a server
+      const bool nobody = rc == ETHCNN_E_IO && strstr(ethcnn_request_error(), "no server") != nullptr;
+      const bool other_weights = rc == ETHCNN_E_FORMAT && strstr(ethcnn_request_error(), "resident handle") != nullptr;
+      if (!nobody && !other_weights) {
         fprintf(stderr, "video_to_cu_depth: server: %s\n", ethcnn_request_error());
         return 1;
       }

@@ -214,15 +214,61 @@ __global__ void gate_export_kernel(const float* __restrict__ src, float* __restr
   dst[i] = v;
 }
 
+// HM's use of one probability (TLibEncoder/TEncCu.cpp:448-457): "> up" = split only (2), "<= down" = no split (0),
+// otherwise both candidates are checked (1).
+__device__ __forceinline__ unsigned decide(float p, float up, float down) { return (p > up) ? 2u : ((p <= down) ? 0u : 1u); }
+
 __global__ void decisions_kernel(const float* __restrict__ prob, unsigned char* __restrict__ dec, long long n_values,
                                  const float* __restrict__ thr6) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n_values) return;
   const int slot = int(i % kProbs);
   const int lvl = slot == 0 ? 0 : (slot < 5 ? 1 : 2);
-  const float up = thr6[2 * lvl], down = thr6[2 * lvl + 1];
-  const float p = prob[i];
-  dec[i] = (p > up) ? 2 : ((p <= down) ? 0 : 1);  // TEncCu.cpp:448-457: "> up" split only, "<= down" no split
+  dec[i] = (unsigned char)decide(prob[i], thr6[2 * lvl], thr6[2 * lvl + 1]);
+}
+
+// GATE + DECISION MAP: the gates as above, the finished float rows written to dst (== src: in place,
+// only the gated slots are touched; != src: every float, consecutive threads on consecutive floats, as gate_export_kernel)
+// and, next to them, HM's threshold rule applied on the device: one 64-bit word per CTU holding 21 two-bit decisions,
+// bits [2k, 2k+1] = decide(row[k]) with k the position in the cu_depth.dat row (0: 64x64, 1..4: 32x32, 5..20: 16x16,
+// TEncCu.cpp:434-447), bits 42..63 zero.  A block handles 256 CTUs through shared memory (row stride 21 words: conflict-free).
+struct Thr6 {
+  float v[6];   // up, down per depth (the AI order of Thr_info.txt, TEncCu.cpp:250)
+};
+constexpr int kMapTile = 256;
+__global__ void __launch_bounds__(kMapTile) gate_map_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                            const unsigned* __restrict__ flags, float t2, long long n_total,
+                                                            int ctus_per_frame, int chunks_per_frame,
+                                                            unsigned long long* __restrict__ map, const Thr6 thr) {
+  __shared__ float rows[kMapTile * kProbs];
+  const long long n0 = blockIdx.x * (long long)kMapTile;
+  const int n_here = int(min((long long)kMapTile, n_total - n0));
+  for (int i = threadIdx.x; i < n_here * kProbs; i += kMapTile) {
+    const int c = i / kProbs, slot = i - c * kProbs;
+    float v = src[n0 * kProbs + i];
+    bool zeroed = false;
+    if (flags != nullptr && slot > 0) {
+      const long long n = n0 + c;
+      const long long f = n / ctus_per_frame;
+      const int r = int(n - f * ctus_per_frame);
+      const unsigned fl = flags[f * chunks_per_frame + r / kSubBatch];
+      const bool g1 = (fl & 1u) != 0;
+      const bool g2 = g1 ? ((fl & 2u) != 0) : (0.0f > t2);
+      if (!((slot < 5) ? g1 : g2)) v = 0.0f, zeroed = true;
+    }
+    if (dst != src || zeroed) dst[n0 * kProbs + i] = v;
+    rows[i] = v;
+  }
+  __syncthreads();
+  if (int(threadIdx.x) < n_here) {
+    const float* r = rows + threadIdx.x * kProbs;
+    unsigned long long m = decide(r[0], thr.v[0], thr.v[1]);
+#pragma unroll
+    for (int k = 1; k < 5; ++k) m |= (unsigned long long)decide(r[k], thr.v[2], thr.v[3]) << (2 * k);
+#pragma unroll
+    for (int k = 5; k < kProbs; ++k) m |= (unsigned long long)decide(r[k], thr.v[4], thr.v[5]) << (2 * k);
+    map[n0 + threadIdx.x] = m;
+  }
 }
 
 }  // namespace
@@ -261,6 +307,16 @@ cudaError_t launch_gate_export(const float* src, float* dst, const unsigned* fla
   if (n_total <= 0) return cudaSuccess;
   const long long work = n_total * kProbs;
   gate_export_kernel<<<unsigned((work + 255) / 256), 256, 0, stream>>>(src, dst, flags, t2, n_total, ctus_per_frame, chunks_per_frame);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gate_map(const float* src, float* dst, const unsigned* flags, float t2, long long n_total, int ctus_per_frame,
+                            int chunks_per_frame, unsigned long long* map, const float thr6[6], cudaStream_t stream) {
+  if (n_total <= 0) return cudaSuccess;
+  Thr6 t;
+  for (int i = 0; i < 6; ++i) t.v[i] = thr6[i];
+  gate_map_kernel<<<unsigned((n_total + kMapTile - 1) / kMapTile), kMapTile, 0, stream>>>(src, dst, flags, t2, n_total, ctus_per_frame,
+                                                                                        chunks_per_frame, map, t);
   return cudaGetLastError();
 }
 

@@ -3,9 +3,10 @@
 //
 // Data flow for one call (per device):
 //   host luma --H2D (copy stream, slabs of whole frames, Y only)--> device slab [frames][H][pitch16]
-//   CONV kernel (TMA tiles) -> features fp16 hi/lo [chunk][2688]  (scratch, chunk = 18944 CTUs)
-//   FC1 kernel -> [chunk][448] fp32 -> HEADS kernel -> raw probabilities + gate flags
-//   GATE kernel over the slab -> D2H of 84 B/CTU into the caller's buffer (its frame range = the "gather")
+//   CONV kernel (mma.sync, TMA tiles) -> features fp16 hi/lo [chunk][2688]   (scratch, chunk = 148 * 256 = 37 888 CTUs)
+//   FC kernel (tcgen05, CTA pairs: FC1 + FC2 + FC3 + sigmoid) -> raw probabilities + gate flags
+//   GATE kernel over the slab (in place; or gate + export to a staged / peer destination; or gate + 2-bit decision map)
+//   D2H of 84 B/CTU (+ 8 B/CTU of decision map) into the caller's buffer (its frame range = the "gather")
 // Slabs (~16 MB of luma) rotate through three buffers so copies overlap kernels.  With n_gpus > 1 one host thread per device
 // runs the same pipeline on a contiguous frame range (video_to_cu_depth.py:88 loop, sharded).
 #include <fcntl.h>
@@ -82,6 +83,7 @@ struct DeviceModel {
   FusedWeights fused;
   int a1_exp = 0, w2_exp = 0;
   std::vector<float> h_b2, h_w2q, h_b3, h_w3q;  // host copies: b2eff / b3eff depend on the call's qp
+  std::string index_bytes;  // the checkpoint's .index file as loaded (holds the crc32c of every tensor): identity of the weights
 };
 
 // One ETH-LSTM checkpoint (HM-16.5_Test_LDP/bin/model_LDP_200000_qp*.dat, 18 tensors) on the device.
@@ -122,6 +124,9 @@ struct DeviceCtx {
   float* d_prob[kSlabs] = {};
   uint8_t* h_stage[kSlabs] = {};
   float* h_prob[kSlabs] = {};
+  unsigned long long* d_map[kSlabs] = {};   // packed decision maps of a slab (ethcnn_predict_luma_map)
+  unsigned long long* h_map[kSlabs] = {};
+  size_t slab_map_words = 0, hmap_words = 0;
   size_t slab_bytes = 0, slab_prob_floats = 0, stage_bytes = 0, hprob_floats = 0;
   cudaEvent_t ev_h2d[kSlabs] = {}, ev_comp[kSlabs] = {}, ev_d2h[kSlabs] = {};
   // profiling
@@ -152,6 +157,8 @@ struct ethcnn_handle {
   std::string model_dir;
   float t1 = 0.5f, t2 = 0.5f;
   bool have_thr = false;
+  float thr6[6] = {0.5f, 0.5f, 0.5f, 0.5f, 0.5f, 0.5f};   // up, down per depth as HM uses them (TEncCu.cpp:250, 448-457)
+  bool have_thr6 = false;
   std::vector<std::unique_ptr<DeviceCtx>> devs;
   std::mutex mu;
   std::atomic<int64_t> launches{0};
@@ -168,7 +175,7 @@ namespace {
 
 // ----------------------------------------------------------------------------------------------
 // Thr_info.txt: first line split on single spaces, tokens [1] and [3] (net_CNN.py:38-45).
-int read_thresholds(const std::string& path, float* t1, float* t2) {
+int read_thresholds(const std::string& path, float* t1, float* t2, float* all6 = nullptr, bool* have6 = nullptr) {
   FILE* f = fopen(path.c_str(), "r");
   if (!f) return fail(ETHCNN_E_IO, "cannot open " + path);
   char line[4096];
@@ -199,6 +206,10 @@ int read_thresholds(const std::string& path, float* t1, float* t2) {
     return true;
   };
   if (!to_float(tok[1], t1) || !to_float(tok[3], t2)) return fail(ETHCNN_E_FORMAT, path + ": tokens [1]/[3] are not numbers");
+  if (all6 && have6) {   // HM itself reads six numbers (fscanf, TEncCu.cpp:250): needed only for the decision map
+    *have6 = tok.size() >= 6;
+    for (int i = 0; i < 6 && *have6; ++i) *have6 = to_float(tok[i], &all6[i]);
+  }
   return ETHCNN_OK;
 }
 
@@ -231,6 +242,17 @@ void free_model(DeviceModel& m) {
   m = DeviceModel();
 }
 
+bool slurp(const std::string& path, std::string* out) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  out->clear();
+  char buf[4096];
+  size_t n;
+  while ((n = fread(buf, 1, sizeof(buf), f)) > 0) out->append(buf, n);
+  fclose(f);
+  return true;
+}
+
 int get_model(ethcnn_handle* h, DeviceCtx& c, int qp, DeviceModel** out) {
   const std::string prefix = model_prefix(h->mode, qp);
   auto it = c.models.find(prefix);
@@ -252,6 +274,7 @@ int get_model(ethcnn_handle* h, DeviceCtx& c, int qp, DeviceModel** out) {
   trace("get_model: packed");
   DeviceModel m;
   int rc;
+  slurp(path + ".index", &m.index_bytes);
   if ((rc = upload(&m.conv, pm.conv.data(), pm.conv.size() * 4))) return rc;
   if ((rc = upload(&m.conv_tc, pm.conv_tc.data(), pm.conv_tc.size()))) return rc;
   for (int br = 0; br < 3; ++br)
@@ -391,9 +414,13 @@ struct LdpStep {             // extra inputs of the LDP CNN + one-step LSTM eval
 };
 
 int run_device(ethcnn_handle* h, DeviceCtx& c, const uint8_t* d_y, int width, int height, size_t pitch, size_t frame_stride,
-               int n_frames, int qp, float* d_out, float* fc1_out, cudaStream_t stream, const LdpStep* ldp = nullptr) {
+               int n_frames, int qp, float* d_out, float* fc1_out, cudaStream_t stream, const LdpStep* ldp = nullptr,
+               unsigned long long* d_map = nullptr) {
   if (width <= 0 || height <= 0 || n_frames < 0 || pitch < size_t(width)) return fail(ETHCNN_E_ARG, "bad frame geometry");
   if (n_frames == 0) return ETHCNN_OK;
+  if (d_map && !h->have_thr6)
+    return fail(ETHCNN_E_FORMAT, "the decision map needs the six thresholds of Thr_info.txt (or ethcnn_set_decision_thresholds)");
+  if (d_map && (fc1_out || !d_out)) return fail(ETHCNN_E_ARG, "the decision map goes with the probability rows");
   CUDA_TRY(cudaSetDevice(c.device));
   DeviceModel* m = nullptr;
   int rc = get_model(h, c, qp, &m);
@@ -534,7 +561,12 @@ int run_device(ethcnn_handle* h, DeviceCtx& c, const uint8_t* d_y, int width, in
       ++h->launches;
     }
   }
-  if (staged) {
+  if (d_map) {   // gates + HM's threshold rule in one pass: float rows (in place or exported) and the packed 2-bit map
+    StageTimer t(c, stream, ETHCNN_STAGE_GATE);
+    CUDA_TRY(launch_gate_map(d_out, final_out, gated ? c.flags : nullptr, h->t2, total, ctus_per_frame, chunks_per_frame, d_map, h->thr6,
+                             stream));
+    ++h->launches;
+  } else if (staged) {
     StageTimer t(c, stream, ETHCNN_STAGE_GATE);
     CUDA_TRY(launch_gate_export(d_out, final_out, gated ? c.flags : nullptr, h->t2, total, ctus_per_frame, chunks_per_frame, stream));
     ++h->launches;
@@ -582,7 +614,24 @@ void parallel_copy_frames(uint8_t* dst, const uint8_t* src, size_t frame_bytes, 
   for (auto& x : th) x.join();
 }
 
-int ensure_staging(DeviceCtx& c, size_t slab_bytes, size_t slab_prob_floats, bool need_stage, bool need_hprob) {
+int ensure_staging(DeviceCtx& c, size_t slab_bytes, size_t slab_prob_floats, bool need_stage, bool need_hprob, size_t map_words = 0,
+                   bool need_hmap = false) {
+  if (map_words > c.slab_map_words) {
+    for (int i = 0; i < DeviceCtx::kSlabs; ++i) {
+      cudaFree(c.d_map[i]);
+      c.d_map[i] = nullptr;
+      CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c.d_map[i]), map_words * 8));
+    }
+    c.slab_map_words = map_words;
+  }
+  if (need_hmap && map_words > c.hmap_words) {
+    for (int i = 0; i < DeviceCtx::kSlabs; ++i) {
+      cudaFreeHost(c.h_map[i]);
+      c.h_map[i] = nullptr;
+      CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&c.h_map[i]), map_words * 8));
+    }
+    c.hmap_words = map_words;
+  }
   if (slab_bytes > c.slab_bytes) {
     for (int i = 0; i < DeviceCtx::kSlabs; ++i) {
       cudaFree(c.d_slab[i]);
@@ -626,7 +675,7 @@ int ensure_staging(DeviceCtx& c, size_t slab_bytes, size_t slab_prob_floats, boo
 // Host-input pipeline on ONE device for frames [0, n_frames) at y / out (already offset by the caller).
 // per_ctu_out = 21 (probabilities) or 448 (FC1 tap).
 int run_host_pipeline(ethcnn_handle* h, DeviceCtx& c, const uint8_t* y, int width, int height, size_t frame_stride,
-                      int n_frames, int qp, float* out, bool fc1_tap) {
+                      int n_frames, int qp, float* out, bool fc1_tap, unsigned long long* map_out = nullptr) {
   if (n_frames <= 0) return ETHCNN_OK;
   CUDA_TRY(cudaSetDevice(c.device));
   const int per_ctu = fc1_tap ? kFc1 : kProbs;
@@ -642,7 +691,9 @@ int run_host_pipeline(ethcnn_handle* h, DeviceCtx& c, const uint8_t* y, int widt
   const bool src_pinned = is_pinned(y);
   const bool dst_pinned = is_pinned(out);
   trace("host pipeline: start");
-  int rc = ensure_staging(c, dev_frame * slab_frames, size_t(slab_frames) * ctus_per_frame * per_ctu, !src_pinned, !dst_pinned);
+  const bool map_pinned = map_out ? is_pinned(map_out) : true;
+  int rc = ensure_staging(c, dev_frame * slab_frames, size_t(slab_frames) * ctus_per_frame * per_ctu, !src_pinned, !dst_pinned,
+                          map_out ? size_t(slab_frames) * ctus_per_frame : 0, !map_pinned);
   if (rc) return rc;
   trace("host pipeline: staging buffers ready");
 
@@ -654,6 +705,8 @@ int run_host_pipeline(ethcnn_handle* h, DeviceCtx& c, const uint8_t* y, int widt
     CUDA_TRY(cudaEventSynchronize(c.ev_d2h[b]));
     if (!dst_pinned)
       memcpy(out + size_t(pend[b].f0) * ctus_per_frame * per_ctu, c.h_prob[b], size_t(pend[b].nf) * ctus_per_frame * per_ctu * 4);
+    if (map_out && !map_pinned)
+      memcpy(map_out + size_t(pend[b].f0) * ctus_per_frame, c.h_map[b], size_t(pend[b].nf) * ctus_per_frame * 8);
     pend[b].slab = -1;
     return ETHCNN_OK;
   };
@@ -682,13 +735,17 @@ int run_host_pipeline(ethcnn_handle* h, DeviceCtx& c, const uint8_t* y, int widt
     CUDA_TRY(cudaEventRecord(c.ev_h2d[b], c.s_h2d));
     CUDA_TRY(cudaStreamWaitEvent(c.s_compute, c.ev_h2d[b], 0));
     rc = run_device(h, c, c.d_slab[b], width, height, pitch, dev_frame, nf, qp, fc1_tap ? nullptr : c.d_prob[b],
-                    fc1_tap ? c.d_prob[b] : nullptr, c.s_compute);
+                    fc1_tap ? c.d_prob[b] : nullptr, c.s_compute, nullptr, map_out ? c.d_map[b] : nullptr);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(c.ev_comp[b], c.s_compute));
     CUDA_TRY(cudaStreamWaitEvent(c.s_d2h, c.ev_comp[b], 0));
     const size_t nfl = size_t(nf) * ctus_per_frame * per_ctu;
     float* dst = dst_pinned ? out + size_t(f0) * ctus_per_frame * per_ctu : c.h_prob[b];
     CUDA_TRY(cudaMemcpyAsync(dst, c.d_prob[b], nfl * 4, cudaMemcpyDeviceToHost, c.s_d2h));
+    if (map_out) {
+      unsigned long long* mdst = map_pinned ? map_out + size_t(f0) * ctus_per_frame : c.h_map[b];
+      CUDA_TRY(cudaMemcpyAsync(mdst, c.d_map[b], size_t(nf) * ctus_per_frame * 8, cudaMemcpyDeviceToHost, c.s_d2h));
+    }
     CUDA_TRY(cudaEventRecord(c.ev_d2h[b], c.s_d2h));
     pend[b].slab = slab_idx, pend[b].f0 = f0, pend[b].nf = nf;
   }
@@ -706,11 +763,12 @@ void frame_range(int n_frames, int n_dev, int r, int* f0, int* nf) {
 }
 
 int run_host_all_devices(ethcnn_handle* h, const uint8_t* y, int width, int height, size_t frame_stride, int n_frames, int qp,
-                         float* out, bool fc1_tap) {
+                         float* out, bool fc1_tap, unsigned long long* map_out = nullptr) {
   const int per_ctu = fc1_tap ? kFc1 : kProbs;
   const size_t ctus_per_frame = size_t((width + kCtu - 1) / kCtu) * ((height + kCtu - 1) / kCtu);
   const int nd = int(h->devs.size());
-  if (nd == 1 || n_frames < 2) return run_host_pipeline(h, *h->devs[0], y, width, height, frame_stride, n_frames, qp, out, fc1_tap);
+  if (nd == 1 || n_frames < 2)
+    return run_host_pipeline(h, *h->devs[0], y, width, height, frame_stride, n_frames, qp, out, fc1_tap, map_out);
   std::vector<int> rcs(nd, 0);
   std::vector<std::string> errs(nd);
   std::vector<std::thread> th;
@@ -719,7 +777,7 @@ int run_host_all_devices(ethcnn_handle* h, const uint8_t* y, int width, int heig
       int f0, nf;
       frame_range(n_frames, nd, r, &f0, &nf);
       rcs[r] = run_host_pipeline(h, *h->devs[r], y + size_t(f0) * frame_stride, width, height, frame_stride, nf, qp,
-                                 out + size_t(f0) * ctus_per_frame * per_ctu, fc1_tap);
+                                 out + size_t(f0) * ctus_per_frame * per_ctu, fc1_tap, map_out ? map_out + size_t(f0) * ctus_per_frame : nullptr);
       if (rcs[r]) errs[r] = g_last_error;
     });
   }
@@ -924,6 +982,7 @@ void close_device(DeviceCtx& c) {
   for (void* p : c.peer_owned) cudaFree(p);
   for (int i = 0; i < DeviceCtx::kSlabs; ++i) {
     cudaFree(c.d_slab[i]), cudaFree(c.d_prob[i]), cudaFreeHost(c.h_stage[i]), cudaFreeHost(c.h_prob[i]);
+    cudaFree(c.d_map[i]), cudaFreeHost(c.h_map[i]);
     if (c.ev_h2d[i]) cudaEventDestroy(c.ev_h2d[i]);
     if (c.ev_comp[i]) cudaEventDestroy(c.ev_comp[i]);
     if (c.ev_d2h[i]) cudaEventDestroy(c.ev_d2h[i]);
@@ -951,8 +1010,18 @@ int create_common(const char* model_dir, const char* thr_path, int mode, const s
   if (const char* e = getenv("ETHCNN_FC1")) h->fc1_path = (strcmp(e, "simt") == 0) ? 0 : (strcmp(e, "tc") == 0 ? 1 : (strcmp(e, "pair") == 0 ? 3 : 2));
   {
     const std::string tp = thr_path ? std::string(thr_path) : h->model_dir + "/Thr_info.txt";
-    int rc = read_thresholds(tp, &h->t1, &h->t2);
+    float tok6[6];
+    bool have6 = false;
+    int rc = read_thresholds(tp, &h->t1, &h->t2, tok6, &have6);
     h->have_thr = (rc == ETHCNN_OK);
+    if (rc == ETHCNN_OK && have6) {
+      // AI file order: up, down per depth (TEncCu.cpp:250); LDP file order: down, up (TEncGOP.cpp(LDP):1449)
+      for (int d = 0; d < 3; ++d) {
+        h->thr6[2 * d] = tok6[2 * d + (mode == ETHCNN_MODE_LDP ? 1 : 0)];
+        h->thr6[2 * d + 1] = tok6[2 * d + (mode == ETHCNN_MODE_LDP ? 0 : 1)];
+      }
+      h->have_thr6 = true;
+    }
     // the AI script cannot run without Thr_info.txt (net_CNN.py:47); the LDP CNN-only entry points can
     if (rc && (mode == ETHCNN_MODE_AI || thr_path)) return rc;
   }
@@ -1010,6 +1079,40 @@ int ethcnn_predict_luma(ethcnn_handle* h, const uint8_t* y, int width, int heigh
   if (width <= 0 || height <= 0 || n_frames < 0 || frame_stride < size_t(width) * height) return fail(ETHCNN_E_ARG, "bad frame geometry");
   std::lock_guard<std::mutex> lock(h->mu);
   return run_host_all_devices(h, y, width, height, frame_stride, n_frames, qp, out, false);
+}
+
+int ethcnn_predict_luma_device_map(ethcnn_handle* h, const uint8_t* d_y, int width, int height, size_t pitch, size_t frame_stride,
+                                   int n_frames, int qp, float* d_out, uint64_t* d_map, void* stream) {
+  if (!h || !d_y || !d_out || !d_map) return fail(ETHCNN_E_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lock(h->mu);
+  return run_device(h, *h->devs[0], d_y, width, height, pitch, frame_stride, n_frames, qp, d_out, nullptr,
+                    static_cast<cudaStream_t>(stream), nullptr, reinterpret_cast<unsigned long long*>(d_map));
+}
+
+int ethcnn_predict_luma_map(ethcnn_handle* h, const uint8_t* y, int width, int height, size_t frame_stride, int n_frames, int qp,
+                            float* out, uint64_t* map) {
+  if (!h || ((!y || !out || !map) && n_frames > 0)) return fail(ETHCNN_E_ARG, "NULL argument");
+  if (width <= 0 || height <= 0 || n_frames < 0 || frame_stride < size_t(width) * height) return fail(ETHCNN_E_ARG, "bad frame geometry");
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (!h->have_thr6)
+    return fail(ETHCNN_E_FORMAT, "the decision map needs the six thresholds of Thr_info.txt (or ethcnn_set_decision_thresholds)");
+  return run_host_all_devices(h, y, width, height, frame_stride, n_frames, qp, out, false, reinterpret_cast<unsigned long long*>(map));
+}
+
+int ethcnn_set_decision_thresholds(ethcnn_handle* h, const float thr6[6]) {
+  if (!h || !thr6) return fail(ETHCNN_E_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lock(h->mu);
+  for (int i = 0; i < 6; ++i) h->thr6[i] = thr6[i];
+  h->have_thr6 = true;
+  return ETHCNN_OK;
+}
+
+int ethcnn_get_decision_thresholds(ethcnn_handle* h, float thr6[6]) {
+  if (!h || !thr6) return fail(ETHCNN_E_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (!h->have_thr6) return fail(ETHCNN_E_FORMAT, "Thr_info.txt did not carry six thresholds");
+  for (int i = 0; i < 6; ++i) thr6[i] = h->thr6[i];
+  return ETHCNN_OK;
 }
 
 int ethcnn_export_fc1(ethcnn_handle* h, const uint8_t* y, int width, int height, size_t frame_stride, int n_frames, float* out) {
@@ -1082,6 +1185,62 @@ int ethcnn_predict_yuv_file(ethcnn_handle* h, const char* yuv_path, int width, i
   return ETHCNN_OK;
 }
 
+int ethcnn_reload_thresholds(ethcnn_handle* h, const char* thr_path) {
+  if (!h) return fail(ETHCNN_E_ARG, "NULL handle");
+  std::lock_guard<std::mutex> lock(h->mu);
+  const std::string tp = (thr_path && *thr_path) ? std::string(thr_path) : h->model_dir + "/Thr_info.txt";
+  float t1, t2, tok6[6];
+  bool have6 = false;
+  int rc = read_thresholds(tp, &t1, &t2, tok6, &have6);
+  if (rc) return rc;
+  h->t1 = t1, h->t2 = t2, h->have_thr = true;
+  h->have_thr6 = have6;
+  for (int d = 0; d < 3 && have6; ++d) {
+    h->thr6[2 * d] = tok6[2 * d + (h->mode == ETHCNN_MODE_LDP ? 1 : 0)];
+    h->thr6[2 * d + 1] = tok6[2 * d + (h->mode == ETHCNN_MODE_LDP ? 0 : 1)];
+  }
+  return ETHCNN_OK;
+}
+
+int ethcnn_predict_yuv_file_from(ethcnn_handle* h, const char* client_dir, const char* yuv_path, int width, int height, int qp,
+                                 const char* out_path) {
+  if (!h || !client_dir || !yuv_path || !out_path) return fail(ETHCNN_E_ARG, "NULL argument");
+  // What the reference script does on EVERY invocation, from the encoder's cwd: read Thr_info.txt (net_CNN.py:47) and restore
+  // the checkpoint of the QP range (video_to_cu_depth.py:126-133).  A resident handle must not answer with stale copies.
+  const std::string dir = *client_dir ? client_dir : ".";
+  int rc = ethcnn_reload_thresholds(h, (dir + "/Thr_info.txt").c_str());
+  if (rc) return rc;
+  const std::string prefix = model_prefix(h->mode, qp);
+  std::string theirs, ours;
+  if (!slurp(dir + "/" + prefix + ".index", &theirs)) return fail(ETHCNN_E_IO, "cannot open " + dir + "/" + prefix + ".index");
+  {
+    std::lock_guard<std::mutex> lock(h->mu);
+    bool stale = false;
+    for (auto& dc : h->devs) {
+      auto it = dc->models.find(prefix);
+      if (it != dc->models.end() && it->second.index_bytes != theirs) stale = true;
+    }
+    if (stale || !slurp(h->model_dir + "/" + prefix + ".index", &ours) || ours != theirs) {
+      // the client's weights are not the ones this handle holds (or would load)
+      char a[4096], b[4096];
+      const bool same_dir = realpath(dir.c_str(), a) && realpath(h->model_dir.c_str(), b) && strcmp(a, b) == 0;
+      if (!same_dir)
+        return fail(ETHCNN_E_FORMAT, "checkpoint " + prefix + " in " + dir + " differs from the one of the resident handle (" + h->model_dir +
+                                         "): run the predictor in-process or start the server in that directory");
+      for (auto& dc : h->devs) {   // same directory, file replaced since it was loaded: drop the resident copy, it is re-read below
+        auto it = dc->models.find(prefix);
+        if (it != dc->models.end()) {
+          cudaSetDevice(dc->device);
+          cudaDeviceSynchronize();
+          free_model(it->second);
+          dc->models.erase(it);
+        }
+      }
+    }
+  }
+  return ethcnn_predict_yuv_file(h, yuv_path, width, height, qp, out_path);
+}
+
 int ethcnn_ldp_step(ethcnn_handle* h, const uint8_t* y, int width, int height, int qp, int i_frame, const float* state_in,
                     float* state_out, float* prob) {
   if (!h || !y || !state_out || !prob) return fail(ETHCNN_E_ARG, "NULL argument");
@@ -1091,6 +1250,18 @@ int ethcnn_ldp_step(ethcnn_handle* h, const uint8_t* y, int width, int height, i
 
 int ethcnn_ldp_serve(ethcnn_handle* h, const char* dir, int max_frames, int idle_timeout_ms) {
   if (!h) return fail(ETHCNN_E_ARG, "NULL handle");
+  // Fail before HM starts waiting on pred_end.sig (its wait is unbounded, TEncGOP.cpp(LDP):1487): the reference daemon dies at
+  // import when Thr_info.txt is missing (net_CNN_LSTM_one_step.py:67-68) and at restore when the CNN checkpoint is.
+  if (h->mode != ETHCNN_MODE_LDP) return fail(ETHCNN_E_ARG, "the LDP daemon requires ETHCNN_MODE_LDP");
+  if (!h->have_thr) return fail(ETHCNN_E_IO, "Thr_info.txt was not found or is malformed: the LDP daemon needs its gate thresholds");
+  {
+    std::lock_guard<std::mutex> lock(h->mu);
+    DeviceCtx& c0 = *h->devs[0];
+    if (cudaSetDevice(c0.device) != cudaSuccess) return fail(ETHCNN_E_CUDA, "cannot select the device");
+    DeviceModel* m0 = nullptr;
+    int rc0 = get_model(h, c0, 32, &m0);   // one CNN checkpoint serves every QP (resi_to_cu_depth_LDP.py:158-159)
+    if (rc0) return rc0;
+  }
   const std::string d = (dir && *dir) ? std::string(dir) + "/" : std::string();
   const std::string start_file = d + "pred_start.sig", end_file = d + "pred_end.sig", command_file = d + "command.dat";
   const std::string yuv_file = d + "resi.yuv", state_file = d + "state.dat", save_file = d + "cu_depth.dat";

@@ -109,6 +109,11 @@ cudaError_t launch_gate(float* prob, const unsigned* flags, float t2, long long 
 cudaError_t launch_gate_export(const float* src, float* dst, const unsigned* flags, float t2, long long n_total,
                                int ctus_per_frame, int chunks_per_frame, cudaStream_t stream);
 
+// Gates + HM's threshold rule on the device: float rows to dst (in place when dst == src) and one 64-bit word of 21 two-bit
+// decisions per CTU to map (dense_stages.cu: gate_map_kernel).  thr6 = up, down per depth.  flags == nullptr: no gates.
+cudaError_t launch_gate_map(const float* src, float* dst, const unsigned* flags, float t2, long long n_total, int ctus_per_frame,
+                            int chunks_per_frame, unsigned long long* map, const float thr6[6], cudaStream_t stream);
+
 // One LSTM step for the three heads (lstm_stage.cu).  state rows are [c(448) | h(448)]; z_scratch is [rows][1792].
 cudaError_t launch_lstm_step(const float* fc1, const float* state_in, float* state_out, float* z_scratch,
                              const float* const kernel[3], const float* const bias[3], int rows, cudaStream_t stream);

@@ -12,9 +12,17 @@
 //   request   "PREDICT\t<cwd>\t<yuv>\t<width>\t<height>\t<qp>\t<out>\n"     relative paths are resolved against <cwd>
 //   reply     "0\n" on success, "<negative ETHCNN_E_* code>\t<message>\n" otherwise
 //   request   "QUIT\n" makes the server return (reply "0\n")
-// The server uses the checkpoints and Thr_info.txt of the directory it was created with (start it in the encoder's bin/).
+// Every PREDICT request is answered through ethcnn_predict_yuv_file_from: Thr_info.txt is re-read from the CLIENT's directory
+// and the client's checkpoint must be the resident one (the reference re-reads both on every run, net_CNN.py:47,
+// video_to_cu_depth.py:126-133) -- a stale threshold or a different model is an error, never a silent answer.
+// Trust: the socket is created 0600, peers are checked with SO_PEERCRED (same uid or root), a connection that sends nothing
+// is dropped after 5 s, and a second server refuses to start on a socket that a live server still answers.
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE   // struct ucred
+#endif
 #include <poll.h>
 #include <sys/socket.h>
+#include <sys/time.h>
 #include <sys/stat.h>
 #include <sys/un.h>
 #include <unistd.h>
@@ -62,7 +70,7 @@ bool read_line(int fd, std::string* line) {
     if (n == 0) return false;
     if (n < 0) {
       if (errno == EINTR) continue;
-      return false;
+      return false;   // includes EAGAIN: the receive timeout of an accepted socket expired
     }
     if (c == '\n') return true;
     line->push_back(c);
@@ -100,10 +108,24 @@ int ethcnn_serve(ethcnn_handle* h, const char* socket_path, int max_requests, in
   if (!h) return ETHCNN_E_ARG;
   sockaddr_un addr;
   if (!fill_addr(socket_path, &addr)) return ETHCNN_E_ARG;
+  {   // is a live server already answering on this path?  Then do not orphan it.
+    const int probe = socket(AF_UNIX, SOCK_STREAM, 0);
+    if (probe >= 0) {
+      const bool alive = connect(probe, reinterpret_cast<sockaddr*>(&addr), sizeof(addr)) == 0;
+      close(probe);
+      if (alive) {
+        g_serve_error = std::string("a live server already listens on ") + socket_path;
+        return ETHCNN_E_IO;
+      }
+    }
+  }
   const int ls = socket(AF_UNIX, SOCK_STREAM, 0);
   if (ls < 0) return ETHCNN_E_IO;
-  unlink(socket_path);   // a stale socket of a dead server
-  if (bind(ls, reinterpret_cast<sockaddr*>(&addr), sizeof(addr)) != 0 || listen(ls, 16) != 0) {
+  unlink(socket_path);   // a stale socket of a dead server (nobody answered the probe above)
+  const mode_t old_mask = umask(0077);   // the socket file is created rw for the owner only
+  const bool bound = bind(ls, reinterpret_cast<sockaddr*>(&addr), sizeof(addr)) == 0;
+  umask(old_mask);
+  if (!bound || chmod(socket_path, 0600) != 0 || listen(ls, 16) != 0) {
     close(ls);
     return ETHCNN_E_IO;
   }
@@ -119,6 +141,18 @@ int ethcnn_serve(ethcnn_handle* h, const char* socket_path, int max_requests, in
     }
     const int cs = accept(ls, nullptr, nullptr);
     if (cs < 0) continue;
+    {   // a client that connects and stays silent must not block everybody else (QUIT included)
+      timeval tv{5, 0};
+      setsockopt(cs, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
+      setsockopt(cs, SOL_SOCKET, SO_SNDTIMEO, &tv, sizeof(tv));
+    }
+    ucred cred{};
+    socklen_t cl = sizeof(cred);
+    if (getsockopt(cs, SOL_SOCKET, SO_PEERCRED, &cred, &cl) != 0 || (cred.uid != geteuid() && cred.uid != 0)) {
+      write_all(cs, std::to_string(ETHCNN_E_ARG) + "\tpeer uid is not the server's\n");
+      close(cs);
+      continue;
+    }
     std::string line, reply;
     if (read_line(cs, &line)) {
       const std::vector<std::string> f = split_tabs(line);
@@ -127,7 +161,7 @@ int ethcnn_serve(ethcnn_handle* h, const char* socket_path, int max_requests, in
         quit = true;
         reply = "0\n";
       } else if (f.size() == 7 && f[0] == "PREDICT" && to_int(f[3], &w) && to_int(f[4], &hgt) && to_int(f[5], &qp)) {
-        const int rc = ethcnn_predict_yuv_file(h, resolve(f[1], f[2]).c_str(), w, hgt, qp, resolve(f[1], f[6]).c_str());
+        const int rc = ethcnn_predict_yuv_file_from(h, f[1].c_str(), resolve(f[1], f[2]).c_str(), w, hgt, qp, resolve(f[1], f[6]).c_str());
         reply = rc == ETHCNN_OK ? std::string("0\n") : std::to_string(rc) + "\t" + ethcnn_last_error() + "\n";
         ++served;
       } else {

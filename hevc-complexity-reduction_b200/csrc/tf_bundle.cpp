@@ -62,7 +62,8 @@ bool read_file(const std::string& path, std::vector<uint8_t>* out, std::string* 
 // One table block: verifies the trailer, returns [begin, limit) of the entry area.
 bool open_block(const std::vector<uint8_t>& buf, uint64_t off, uint64_t size, const uint8_t** begin, size_t* limit,
                 std::string* err) {
-  if (off + size + 5 > buf.size() || size < 4) {
+  // overflow-safe: the handle comes from the file, off + size + 5 may wrap
+  if (size < 4 || buf.size() < 5 || size > buf.size() - 5 || off > buf.size() - 5 - size) {
     *err = "table block outside file";
     return false;
   }
@@ -95,7 +96,7 @@ bool for_each_entry(const uint8_t* b, size_t limit, std::string* err, Fn fn) {
   while (pos < limit) {
     uint64_t shared, non_shared, vlen;
     if (!get_varint(b, limit, &pos, &shared) || !get_varint(b, limit, &pos, &non_shared) ||
-        !get_varint(b, limit, &pos, &vlen) || shared > key.size() || pos + non_shared + vlen > limit) {
+        !get_varint(b, limit, &pos, &vlen) || shared > key.size() || non_shared > limit - pos || vlen > limit - pos - non_shared) {
       *err = "corrupt table entry";
       return false;
     }
@@ -134,7 +135,7 @@ bool walk_proto(const uint8_t* p, size_t n, Fn on_field) {
       pos += 8;
     } else if (wt == 2) {
       uint64_t l;
-      if (!get_varint(p, n, &pos, &l) || pos + l > n) return false;
+      if (!get_varint(p, n, &pos, &l) || l > n - pos) return false;
       bp = p + pos;
       bl = size_t(l);
       pos += l;
@@ -273,8 +274,15 @@ bool read_tf_bundle(const std::string& prefix, std::map<std::string, BundleTenso
       return false;
     }
     uint64_t n = 1;
-    for (int64_t d : e.shape) n *= uint64_t(d);
-    if (e.shard != 0 || e.size != 4 * n || e.offset + e.size > data.size()) {
+    bool dims_ok = true;
+    for (int64_t d : e.shape) {   // no negative dims, no element count beyond what the data file could hold
+      if (d < 0 || (d > 0 && n > data.size() / uint64_t(d))) {
+        dims_ok = false;
+        break;
+      }
+      n *= uint64_t(d);
+    }
+    if (!dims_ok || e.shard != 0 || n > data.size() / 4 || e.size != 4 * n || e.size > data.size() || e.offset > data.size() - e.size) {
       *err = "tensor " + kv.first + ": bad extent";
       return false;
     }

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define ETHCNN_ABI_VERSION 3 /* 2: staged output option + peer gather buffers; 3: resident server */
+#define ETHCNN_ABI_VERSION 4 /* 2: staged output option + peer gather buffers; 3: resident server; 4: decision map */
 
 /* Which network/deployment is evaluated. */
 #define ETHCNN_MODE_AI  0 /* HM-16.5_Test_AI/bin/net_CNN.py:103-195 (x/255, qp/51, batch-level gates)      */
@@ -128,15 +128,48 @@ int ethcnn_ldp_serve(ethcnn_handle* h, const char* dir, int max_frames, int idle
  * TensorFlow with a resident daemon for its inter-mode path (README.md:64-84).  ethcnn_serve keeps the handle (context, packed
  * weights, scratch) alive and answers requests on a Unix-domain stream socket until max_requests (> 0) PREDICT requests have
  * been served, nothing arrived for idle_timeout_ms (> 0) or a client asked it to quit; returns the number of requests served
- * (>= 0) or a negative code.  It uses the checkpoints / Thr_info.txt of the directory the handle was created with; relative
- * paths of a request are resolved against the CLIENT's working directory.  Protocol: csrc/serve.cpp.
+ * (>= 0) or a negative code.  Every request re-reads the CLIENT directory's Thr_info.txt and checks its checkpoint against the
+ * resident one (ethcnn_predict_yuv_file_from below); relative paths are resolved against the client's working directory.  The
+ * socket is created with mode 0600 and only peers with the server's uid (or root) are served; a second server on a socket that a
+ * live server answers refuses to start (ETHCNN_E_IO).  Protocol: csrc/serve.cpp.
  * ethcnn_request is the client (no handle, no CUDA): returns the server's code for ethcnn_predict_yuv_file, or ETHCNN_E_IO when
  * nobody listens on socket_path (the CLI and the Python shim then work in-process); ethcnn_request_error() has the message.
  */
 int ethcnn_serve(ethcnn_handle* h, const char* socket_path, int max_requests, int idle_timeout_ms);
+
+/*
+ * What a RESIDENT handle must redo per request to behave like a fresh run of the reference script from `client_dir` (the
+ * encoder's cwd): re-read <client_dir>/Thr_info.txt (net_CNN.py:47 reads it at every invocation, and HM reads the same file
+ * itself, TEncCu.cpp:250) and make sure the checkpoint of the QP range in client_dir (video_to_cu_depth.py:126-133) is the one
+ * the handle holds: the .index files (which carry the crc32c of every tensor) must be identical, otherwise the call fails with
+ * ETHCNN_E_FORMAT -- or, when client_dir IS the handle's model directory and the file was replaced, the resident copy is dropped
+ * and re-read.  Then ethcnn_predict_yuv_file.  ethcnn_serve answers every request through this.
+ * ethcnn_reload_thresholds re-reads a Thr_info.txt (NULL = <model_dir>/Thr_info.txt) into the handle.
+ */
+int ethcnn_predict_yuv_file_from(ethcnn_handle* h, const char* client_dir, const char* yuv_path, int width, int height, int qp,
+                                 const char* out_path);
+int ethcnn_reload_thresholds(ethcnn_handle* h, const char* thr_path);
 int ethcnn_request(const char* socket_path, const char* yuv_path, int width, int height, int qp, const char* out_path);
 int ethcnn_request_quit(const char* socket_path);
 const char* ethcnn_request_error(void);
+
+/*
+ * Decision map: HM's threshold rule (TLibEncoder/TEncCu.cpp:434-462) applied ON THE DEVICE by the
+ * gate kernel, next to the float rows.  One 64-bit word per CTU: bits [2k, 2k+1] hold the decision for entry k of the CTU's
+ * cu_depth.dat row (k = 0: the 64x64 CU; 1 + x/32 + 2 (y/32): 32x32; 5 + x/16 + 4 (y/16): 16x16 -- the indices HM computes at
+ * TEncCu.cpp:434-447): 2 = split only (p > up), 0 = no split (p <= down), 1 = check both; bits 42..63 are zero.  8 bytes per
+ * CTU instead of 84.  The thresholds are the six numbers of Thr_info.txt read at create (AI file order up,down per depth,
+ * TEncCu.cpp:250; LDP file order down,up, TEncGOP.cpp(LDP):1449) unless replaced with ethcnn_set_decision_thresholds
+ * (thr6 = up0, down0, up1, down1, up2, down2).  The float rows are produced exactly as by the calls without _map.
+ *   ethcnn_predict_luma_map          host pointers (out: n*21 floats, map: n words)
+ *   ethcnn_predict_luma_device_map   device pointers, enqueued on `stream`, not synchronised
+ */
+int ethcnn_predict_luma_map(ethcnn_handle* h, const uint8_t* y, int width, int height, size_t frame_stride, int n_frames, int qp,
+                            float* out, uint64_t* map);
+int ethcnn_predict_luma_device_map(ethcnn_handle* h, const uint8_t* d_y, int width, int height, size_t pitch, size_t frame_stride,
+                                   int n_frames, int qp, float* d_out, uint64_t* d_map, void* stream);
+int ethcnn_set_decision_thresholds(ethcnn_handle* h, const float thr6[6]);
+int ethcnn_get_decision_thresholds(ethcnn_handle* h, float thr6[6]);
 
 /* HM's use of a probability (TLibEncoder/TEncCu.cpp:448-462): 2 = split only (p > up), 0 = no split
  * (p <= down), 1 = check both.  thr6 = the six numbers of Thr_info.txt (up,down per depth,

@@ -266,6 +266,7 @@ def test_resident_server_serves_the_drop_in(eb, ai_model_dir, tmp_path):
     W, H, nf, qp = 200, 136, 3, 32
     work = tmp_path / "encoder_cwd"
     work.mkdir()
+    assets.materialize(str(work), "AI")      # the encoder's bin/: checkpoints + Thr_info.txt, as the reference script needs them
     (work / "clip.yuv").write_bytes(eo.synth_yuv(W, H, nf, seed0=7))
     with eb.EthCnn(d, None, eb.MODE_AI, device=0) as net:
         net.predict_yuv_file(str(work / "clip.yuv"), W, H, qp, str(work / "want.dat"))
@@ -296,6 +297,38 @@ def test_resident_server_serves_the_drop_in(eb, ai_model_dir, tmp_path):
         assert r.returncode == 1 and b"whole number" in r.stderr
         r = subprocess.run([cli, "clip.yuv", str(W), str(H), str(qp)], cwd=str(work), env=env, capture_output=True)
         assert r.returncode == 0
+        # the operating point is edited between two encodes: the server re-reads the CLIENT's Thr_info.txt per request
+        # (net_CNN.py:47 does, and HM reads the same file, TEncCu.cpp:250) -- no stale gates
+        (work / "Thr_info.txt").write_text("0.9 2.0 0.9 2.0 0.9 2.0")
+        r = subprocess.run([cli, "clip.yuv", str(W), str(H), str(qp)], cwd=str(work), env=env, capture_output=True)
+        assert r.returncode == 0, r.stderr.decode()
+        gated = np.frombuffer((work / "cu_depth.dat").read_bytes(), "<f4").reshape(-1, 21)
+        plain = np.frombuffer(want, "<f4").reshape(-1, 21)
+        assert (gated[:, 1:] == 0).all() and np.array_equal(gated[:, 0], plain[:, 0])
+        (work / "Thr_info.txt").write_text("0.5 0.5 0.5 0.5 0.5 0.5")
+        # a second server on the same socket refuses to start instead of orphaning the live one
+        second = subprocess.run([cli, "--serve", sock, "500"], cwd=d, capture_output=True, timeout=120)
+        assert second.returncode == 1
+        # an encoder directory holding OTHER weights: the server refuses to answer with its own, the drop-in works in-process
+        other = tmp_path / "other_bin"
+        other.mkdir()
+        w2 = eo.random_weights(77)
+        for name in assets.AI_MODELS.values():
+            tf_bundle.write_bundle(str(other / name), w2)
+        (other / "Thr_info.txt").write_text("0.5 0.5 0.5 0.5 0.5 0.5")
+        (other / "clip.yuv").write_bytes((work / "clip.yuv").read_bytes())
+        r = subprocess.run([cli, "clip.yuv", str(W), str(H), str(qp)], cwd=str(other), env=env, capture_output=True)
+        assert r.returncode == 0 and b"in-process" in r.stderr, r.stderr.decode()
+        got2 = np.frombuffer((other / "cu_depth.dat").read_bytes(), "<f4").reshape(-1, 21)
+        check(got2, eo.get_prob((work / "clip.yuv").read_bytes(), W, H, qp, w2, eo.MODE_AI, (0.5, 0.5)), what="other weights, in-process")
+        # a silent client does not block the others (receive timeout on accepted sockets)
+        import socket as pysock
+        mute = pysock.socket(pysock.AF_UNIX, pysock.SOCK_STREAM)
+        mute.connect(sock)
+        t = time.time()
+        r = subprocess.run([cli, "clip.yuv", str(W), str(H), str(qp)], cwd=str(work), env=env, capture_output=True, timeout=60)
+        assert r.returncode == 0 and time.time() - t < 20
+        mute.close()
         assert subprocess.run([cli, "--quit", sock]).returncode == 0
         assert srv.wait(timeout=30) == 0
     finally:

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(eb):
     assert len(names) >= 19
     for n in names:
         assert hasattr(lib, n), "library lacks %s declared in include/ethcnn.h" % n
-    assert lib.ethcnn_abi_version() == 3
+    assert lib.ethcnn_abi_version() == 4
 
 
 def test_missing_library_fails_loudly(eb, monkeypatch, tmp_path):
