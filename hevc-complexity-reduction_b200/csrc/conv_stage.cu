@@ -252,35 +252,43 @@ __device__ __forceinline__ void warp_task(const int pool, const uint32_t wb, con
   uint32_t keep_h[6], keep_l[6];   // set A's conv2 outputs of the current region pair, waiting for set B's
 #pragma unroll
   for (int i = 0; i < 6; ++i) keep_h[i] = keep_l[i] = 0u;
-  float2 ba_lo = b1lo, ba_hi = b1hi, bb_lo = b1lo, bb_hi = b1hi;   // conv1 bias + mean term of the quad, sets A / B
+  // conv1 bias + mean term of the quad, sets A / B.  W = integer sum over the quad's 16x16 pooled window (256 pool^2 pixels)
+  // from the 16x16-pixel block sums the producer warp tabulated; the mean term (centre - W/256) * 256/32 = 8 centre - W/32 is
+  // exact in fp32.  Done for both sets up front, where its latency (LDS -> shuffles -> I2F -> FFMA) hides behind the first
+  // pixel loads instead of sitting at the head of two iterations of the rolled loop below.
+  float2 ba_lo, ba_hi, bb_lo, bb_hi;
+  {
+    uint32_t wsa, wsb;
+    if (pool == 4) {
+      const uint4 va = lds_u128(qa.wsum), vb = lds_u128(qb.wsum);
+      wsa = va.x + va.y + va.z + va.w, wsb = vb.x + vb.y + vb.z + vb.w;
+    } else {
+      wsa = lds_u32(qa.wsum), wsb = lds_u32(qb.wsum);
+    }
+    if (pool != 1) {
+      wsa += __shfl_xor_sync(0xffffffffu, wsa, 1), wsb += __shfl_xor_sync(0xffffffffu, wsb, 1);
+      wsa += __shfl_xor_sync(0xffffffffu, wsa, 2), wsb += __shfl_xor_sync(0xffffffffu, wsb, 2);
+    }
+    const float centre = float(1024 * pool * pool);
+    const float mua = fmaf(__uint2float_rn(wsa), -0.03125f, centre) * u1, mub = fmaf(__uint2float_rn(wsb), -0.03125f, centre) * u1;
+    ba_lo = fma2(make_float2(mua, mua), t1lo, b1lo), ba_hi = fma2(make_float2(mua, mua), t1hi, b1hi);
+    bb_lo = fma2(make_float2(mub, mub), t1lo, b1lo), bb_hi = fma2(make_float2(mub, mub), t1hi, b1hi);
+  }
 
-  // (region pair T, set st) = (it / 2, it % 2); rolled so that the loop body stays inside the instruction cache
-#pragma unroll 1
+  // (region pair T, set st) = (it / 2, it % 2).  Unrolled by two: the pixel loads and conv1 MMAs of the second half overlap the
+  // conv2 epilogue / stores of the first (0.186 -> 0.178 ms per 25 500 CTUs); fully unrolled the body no longer fits the
+  // instruction cache (0.190 ms) -- profiles/r02c_conv_variants.md.
+#ifndef ETHCNN_CONV_IT_UNROLL
+#define ETHCNN_CONV_IT_UNROLL 2
+#endif
+  constexpr int kItUnroll = ETHCNN_CONV_IT_UNROLL;
+#pragma unroll kItUnroll
   for (int it = 0; it < 4; ++it) {
     const int T = it >> 1, st = it & 1;
     const uint32_t blk = st ? qb.blk : qa.blk;
     __half* const hi = st ? qb.hi : qa.hi;
     __half* const lo = st ? qb.lo : qa.lo;
     const int c2_off = st ? qb.c2_off : qa.c2_off;
-    if (T == 0) {
-      // W = integer sum over the quad's 16x16 pooled window (256 pool^2 pixels) from the 16x16-pixel block sums the
-      // producer warp tabulated; the mean term (centre - W/256) * 256/32 = 8 centre - W/32 is exact in fp32
-      uint32_t ws;
-      if (pool == 4) {
-        const uint4 v = lds_u128(st ? qb.wsum : qa.wsum);
-        ws = v.x + v.y + v.z + v.w;
-      } else {
-        ws = lds_u32(st ? qb.wsum : qa.wsum);
-      }
-      if (pool != 1) {
-        ws += __shfl_xor_sync(0xffffffffu, ws, 1);
-        ws += __shfl_xor_sync(0xffffffffu, ws, 2);
-      }
-      const float mu = fmaf(__uint2float_rn(ws), -0.03125f, float(1024 * pool * pool)) * u1;
-      const float2 mu2 = make_float2(mu, mu);
-      const float2 lo2 = fma2(mu2, t1lo, b1lo), hi2 = fma2(mu2, t1hi, b1hi);
-      if (st) bb_lo = lo2, bb_hi = hi2; else ba_lo = lo2, ba_hi = hi2;
-    }
     const float2 be_lo = st ? bb_lo : ba_lo, be_hi = st ? bb_hi : ba_hi;
     PH_MARK(phb, 0);   // task set-up / window sums
     uint32_t xh[16];
@@ -289,6 +297,11 @@ __device__ __forceinline__ void warp_task(const int pool, const uint32_t wb, con
     float d2[3][4];
 #pragma unroll
     for (int nt = 0; nt < 3; ++nt) d2[nt][0] = d2[nt][1] = d2[nt][2] = d2[nt][3] = 0.f;
+#ifdef ETHCNN_CONV_SPLIT_ACC   // correction passes (hi*lo, lo*hi) into their own accumulators: dependent chains of 4 + 8 instead of 12
+    float e2[3][4];
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt) e2[nt][0] = e2[nt][1] = e2[nt][2] = e2[nt][3] = 0.f;
+#endif
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       // conv1 for patch p of regions 2T (row g) and 2T+1 (row g+8): the A operand is exact, two passes (B hi, B lo)
@@ -310,9 +323,21 @@ __device__ __forceinline__ void warp_task(const int pool, const uint32_t wb, con
       for (int nt = 0; nt < 3; ++nt) {
         const uint2 wh = lds_u64(wb + 4 * kF2HiOff + ((p * 3 + nt) * 32 + lane) * 8);
         const uint2 wl = lds_u64(wb + 4 * kF2LoOff + ((p * 3 + nt) * 32 + lane) * 8);
+#ifdef ETHCNN_CONV_SPLIT_ACC
+        mma16816(d2[nt], a2h, wh);
+        mma16816(e2[nt], a2h, wl);
+        mma16816(e2[nt], a2l, wh);
+#else
         mma3(d2[nt], a2h, a2l, wh, wl);
+#endif
       }
     }
+#ifdef ETHCNN_CONV_SPLIT_ACC
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) d2[nt][i] += e2[nt][i];
+#endif
     PH_MARK(phb, 2);   // conv1 + epilogue + conv2 MMAs
     // conv2 outputs of regions 2T (c0, c1) and 2T+1 (c2, c3): features (already scaled by 2^feat_exp, hi/lo)
     uint32_t cur_h[6], cur_l[6];   // pair index 3 (r - 2T) + nt
