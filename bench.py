@@ -44,8 +44,8 @@ ALG_FLOP_PER_CTU = 3104298              # 2 * 1 552 149 MAC
 CONV_FLOP_PER_CTU = 2 * 279552
 SCRATCH_BYTES_PER_CTU = 2 * 2 * 2688    # the features as fp16 hi + lo, written by the conv kernel and read by the FC kernel
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch, per CTU, from the `ncu --set full` captures under profiles/
-NCU_DRAM_BYTES_PER_CTU = {"conv": (104.451328e6 + 223.326720e6) / 25500, "fc1": (290.425600e6 + 5.473792e6) / 25500}
-NCU_DRAM_SOURCE = {"conv": "profiles/r01h_conv_v4.md", "fc1": "profiles/r01h_fc_pair.md"}
+NCU_DRAM_BYTES_PER_CTU = {"conv": (104.595200e6 + 224.020736e6) / 25500, "fc1": (290.185728e6 + 5.063936e6) / 25500}
+NCU_DRAM_SOURCE = {"conv": "profiles/r02e_conv.md", "fc1": "profiles/r02e_fc_pair.md"}
 
 MODE_AI, MODE_LDP = 0, 1
 CONFIGS = {
