@@ -530,6 +530,73 @@ def roofline_of(res, peaks):
     return out
 
 
+def drop_in_wallclock(model_dir, cfg):
+    """Wall clock of the drop-in the way HM uses it (TAppEncCfg.cpp:2319 forks one process per encode) on the config's file:
+    the C++ CLI working in-process (pays CUDA start-up) and as a client of the resident server (`--serve`), plus the Python
+    shim as a client.  Everything inside: process start, file read, H2D, kernels, D2H, the cu_depth.dat write."""
+    pkg = os.path.join(ROOT, "hevc-complexity-reduction_b200")
+    cli = os.path.join(pkg, "bin", "video_to_cu_depth")
+    if not os.path.exists(cli):
+        return None
+    work = model_dir
+    W, H, nf = cfg["w"], cfg["h"], cfg["frames"]
+    yuv = os.path.join(work, "bench_clip.yuv")
+    clip = clip_frames(cfg, 0, nf, 4242)
+    uv = bytes([128]) * (W * H // 2)
+    with open(yuv, "wb") as f:
+        for k in range(nf):
+            f.write(clip[k].tobytes())
+            f.write(uv)
+    shim = os.path.join(work, "video_to_cu_depth.py")
+    if not os.path.lexists(shim):
+        os.symlink(os.path.join(pkg, "video_to_cu_depth.py"), shim)
+    n = nf * ctus_per_frame(cfg)
+    argv = ["bench_clip.yuv", str(W), str(H), str(cfg["qps"][min(2, len(cfg["qps"]) - 1)])]
+    env = dict(os.environ)
+    env.pop("ETHCNN_SERVER", None)
+
+    def once(cmd, e):
+        out = os.path.join(work, "cu_depth.dat")
+        if os.path.exists(out):
+            os.remove(out)
+        t = time.time()
+        r = subprocess.run(cmd, cwd=work, env=e, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+        dt = time.time() - t
+        if r.returncode != 0 or os.path.getsize(out) != n * 84:
+            raise RuntimeError("drop-in failed: " + r.stderr.decode()[-300:])
+        return dt
+    res = {"file": "%dx%d x %d frames (%.1f MB of 4:2:0)" % (W, H, nf, os.path.getsize(yuv) / 1e6), "ctus": n}
+    try:
+        res["cli_in_process_s"] = once([cli] + argv, env)
+        sock = os.path.join(work, "bench.sock")
+        srv = subprocess.Popen([cli, "--serve", sock], cwd=work, stderr=subprocess.DEVNULL)
+        try:
+            for _ in range(1200):
+                if os.path.exists(sock) or srv.poll() is not None:
+                    break
+                time.sleep(0.05)
+            e2 = dict(env, ETHCNN_SERVER=sock)
+            once([cli] + argv, e2)   # first request loads the checkpoint
+            res["cli_to_resident_server_s"] = min(once([cli] + argv, e2) for _ in range(3))
+            res["python_shim_to_resident_server_s"] = min(once([sys.executable, "video_to_cu_depth.py"] + argv, e2) for _ in range(2))
+            res["ctu_per_s_through_the_server"] = n / res["cli_to_resident_server_s"]
+        finally:
+            subprocess.run([cli, "--quit", sock], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            try:
+                srv.wait(timeout=30)
+            except Exception:
+                srv.kill()
+    except Exception as e:   # a measurement, not a gate
+        res["error"] = str(e)[:200]
+    finally:
+        for fn in ("bench_clip.yuv", "cu_depth.dat"):
+            try:
+                os.remove(os.path.join(work, fn))
+            except OSError:
+                pass
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -564,6 +631,7 @@ def run_ours(args):
             synthetic += synth.prepare_models(model_dirs[mode], "LDP" if mode == MODE_LDP else "AI")
             cx.nets[mode] = eb.EthCnn(model_dirs[mode], None, eb.MODE_LDP if mode == MODE_LDP else eb.MODE_AI, device=local)
 
+    dense_path_id = cx.nets[CONFIGS[main_id]["mode"]].query(3)
     sampler = ClockSampler(local).start()   # from the warm-up to the end of the headline's e2e region (both under load)
     main = measure_config(cx, main_id, args.steps, args.warmup, want_e2e=True, want_check=True,
                           sustain_s=0.0, h2d_probe=True)
@@ -622,8 +690,14 @@ def run_ours(args):
                             "sample": "%d frames of %dx%d at QP %d (oracle port, one worker process per core)" % (n, cfg["w"], cfg["h"], qp_b)}
             ref.close()
 
+        drop_in = None
+        if world == 1 and args.config is None and not args.only_main:
+            for net in cx.nets.values():   # the CLI / server below open their own handles
+                net.close()
+            cx.nets_closed = True
+            drop_in = drop_in_wallclock(model_dirs[cfg["mode"]], cfg)
         dense = ("simt", "tcgen05 FC1 + heads kernel", "fused tcgen05 FC1+FC2+FC3",
-                 "fused tcgen05 FC1+FC2+FC3 on CTA pairs (cta_group::2)")[cx.nets[cfg["mode"]].query(3)]
+                 "fused tcgen05 FC1+FC2+FC3 on CTA pairs (cta_group::2)")[dense_path_id]
         line = {
             "metric": "CTUs/sec (ETH-CNN inference)", "value": main["value"], "unit": "CTU/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": cfg["scaling"],
@@ -647,11 +721,13 @@ def run_ours(args):
             "timed_region_s": main["timed_region_s"],
             "sustained": sustained or None,
             "other_configs": others or None,
+            "drop_in_wallclock": drop_in,
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line))
-    for net in cx.nets.values():
-        net.close()
+    if not getattr(cx, "nets_closed", False):
+        for net in cx.nets.values():
+            net.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
