@@ -405,6 +405,7 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
   uint64_t* full = reinterpret_cast<uint64_t*>(sums + kConvStages * kSumWords);   // tile bytes landed
   uint64_t* empty = full + kConvStages;                                           // all warp tasks of the group done
   uint64_t* ready = empty + kConvStages;                                          // block sums of the group tabulated
+  unsigned int* next_task = reinterpret_cast<unsigned int*>(ready + kConvStages);   // warp-task dispenser of this CTA
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef ETHCNN_EXP_TIMING
@@ -421,6 +422,7 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
       mbar_init(&empty[s], kGroupTasks);
       mbar_init(&ready[s], 1);
     }
+    *next_task = 0;
     mbar_fence_init();
   }
   __syncthreads();
@@ -490,11 +492,16 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
       if (lane == 0) mbar_arrive(&ready[stage]);
     }
   } else {
-    // ---------------- compute warps: warp tasks round-robin ----------------
-    const int cw = warp - 1;
+    // ---------------- compute warps: warp tasks from a dispenser ----------------
+    // Tasks are handed out in order from a shared counter instead of round-robin: M / L tasks cost 1.2 - 1.6x an S task, and
+    // with a static assignment the warps that keep drawing them set the pace while the others wait on the 2-deep ring
+    // (9.6 % of the compute warps' time, profiles/r02a_conv_ablation.md).
     const uint32_t wsm_addr = smem_u32(wsm);
     const int g = lane >> 2;
-    for (int t = cw;; t += kConvComputeWarps) {
+    for (;;) {
+      int t = 0;
+      if (lane == 0) t = int(atomicAdd(next_task, 1u));
+      t = __shfl_sync(0xffffffffu, t, 0);
       // the four M and the L task of a group take longest (pooling on the fly): they go first, the 16 S tasks fill up
       const int j = t / kGroupTasks, task = (t - j * kGroupTasks + 16) % kGroupTasks;
       const int grp = blockIdx.x + j * gridDim.x;
