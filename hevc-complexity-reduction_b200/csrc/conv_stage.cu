@@ -212,6 +212,25 @@ __shared__ unsigned int s_conv_phase[16][24];
 #define PH_MARK(br, k)
 #endif
 
+#ifdef ETHCNN_EXP_UMMA_LOAD   // measurement only: the producer warp issues dummy tcgen05 MMAs (what a fused FC1 would put on
+                              // the tensor pipe) while the compute warps run the unchanged conv stage
+__device__ __forceinline__ void exp_umma(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+  asm volatile(
+      "{\n.reg .pred p, e;\n.reg .b32 rx;\nelect.sync rx|e, 0xffffffff;\nsetp.ne.b32 p, 1, 0;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t exp_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr & 0x3ffffu) >> 4);
+  d |= uint64_t(1) << 16;
+  d |= uint64_t(1024 >> 4) << 32;
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(2) << 61;
+  return d;
+}
+#endif
+
 struct QuadSet {        // what a lane needs to know about its quad in set A or B
   uint32_t blk;         // shared-memory address of the quad's pixel block inside its CTU tile
   uint32_t wsum;        // shared-memory address of this lane's share of the quad's window sum (block-sum table)
@@ -416,7 +435,18 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
     float4* dst = reinterpret_cast<float4*>(wsm);
     for (int i = threadIdx.x; i < kConvFloats / 4; i += kConvThreads) dst[i] = src[i];
   }
+#ifdef ETHCNN_EXP_UMMA_LOAD
+  __shared__ uint32_t exp_tmem_slot;
+  __shared__ uint64_t exp_bar;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&exp_tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+#endif
   if (threadIdx.x == 0) {
+#ifdef ETHCNN_EXP_UMMA_LOAD
+    mbar_init(&exp_bar, 1);
+#endif
     for (int s = 0; s < kConvStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], kGroupTasks);
@@ -490,7 +520,26 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&ready[stage]);
+#ifdef ETHCNN_EXP_UMMA_LOAD
+      {   // ETHCNN_EXP_UMMA_LOAD dummy MMAs (M = 128, N = 224, K = 16: 112 cycles each) per 16-CTU group, in bursts of 6 like the
+          // K = 16 stages of a fused FC1 (930 tensor cycles per CTU = 133 such MMAs per group)
+        const uint32_t tm = exp_tmem_slot;
+        const uint64_t da = exp_desc(smem_u32(tiles)), db = exp_desc(smem_u32(tiles) + 16384);
+        const uint32_t idesc = (1u << 4) | (uint32_t(224 >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+        for (int b = 0; b < ETHCNN_EXP_UMMA_LOAD; b += 6) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) exp_umma(tm, da + uint64_t(2 * (k & 3)), db + uint64_t(2 * (k & 3)), idesc);
+          __nanosleep(ETHCNN_EXP_UMMA_SLEEP);
+        }
+      }
+#endif
     }
+#ifdef ETHCNN_EXP_UMMA_LOAD
+    asm volatile("{\n.reg .pred e;\n.reg .b32 rx;\nelect.sync rx|e, 0xffffffff;\n"
+                 "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(smem_u32(&exp_bar)) : "memory");
+    mbar_wait(&exp_bar, 0);
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(exp_tmem_slot), "r"(512));
+#endif
   } else {
     // ---------------- compute warps: warp tasks from a dispenser ----------------
     // Tasks are handed out in order from a shared counter instead of round-robin: M / L tasks cost 1.2 - 1.6x an S task, and
