@@ -39,7 +39,12 @@ constexpr int kRowBytes = kBK * 2;
 constexpr int kABytes = kBM * kRowBytes;                     // 16384 | 8192
 constexpr int kKSteps = kFeat / kBK;                         // 42 | 84
 constexpr int kAcc2Col = 256;                                // TMEM column of accumulator 2
-constexpr int kThreads = 192;
+#ifndef ETHCNN_FC_EPI_WARPS
+#define ETHCNN_FC_EPI_WARPS 8
+#endif
+constexpr int kEpiWarps = ETHCNN_FC_EPI_WARPS;                // 4: one warp per TMEM lane quarter; 8: two, splitting the columns of epi1
+static_assert(kEpiWarps == 4 || kEpiWarps == 8, "epilogue warps come in sets of four (one per TMEM lane quarter)");
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kW3Floats = 48 * 1 + 96 * 4 + 192 * 16;        // 3504
 constexpr int kTableFloats = kW3Floats + 336 + 21 + kFc1 + 3; // w3 | b2eff | b3eff | b1 (padded to 16 B)
 // kCtas = 1: one CTA per 128-CTU tile.  kCtas = 2: a CTA PAIR (cluster of two, tcgen05 cta_group::2) per 256-CTU tile;
@@ -239,8 +244,8 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a_hi), prefetch_tmap(&map_a_lo);
     prefetch_tmap(&w1_hi_t0), prefetch_tmap(&w1_lo_t0), prefetch_tmap(&w1_hi_t1), prefetch_tmap(&w1_lo_t1);
-    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 2), mbar_init(&empty[s], 1), mbar_init(&a2_full[s], 4 * kCtas);
-    mbar_init(acc1_full, 1), mbar_init(acc1_empty, 4 * kCtas), mbar_init(acc2_full, 1), mbar_init(acc2_empty, 4 * kCtas);
+    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 2), mbar_init(&empty[s], 1), mbar_init(&a2_full[s], kEpiWarps * kCtas);
+    mbar_init(acc1_full, 1), mbar_init(acc1_empty, kEpiWarps * kCtas), mbar_init(acc2_full, 1), mbar_init(acc2_empty, 4 * kCtas);
     mbar_fence_init();
   }
   if (warp == 1) {   // the same warp of both CTAs of a pair allocates collectively
@@ -381,6 +386,9 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
   } else {
     // ------------------------------------------------ epilogue warps ------------------------------------------------
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    // with eight epilogue warps the two warps of a quarter split the columns of every a1 slice (the drain of accumulator 1 sits
+    // between FC1(i) and FC2(i) on the tensor pipe's critical path); accumulator 2 is drained by the first set only
+    const int cset = (warp - 2) >> 2;       // 0 | 1
     const int row_l = q * 32 + lane;        // row inside the tile = TMEM lane
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     int it = 0, tile_i = 0;
@@ -398,7 +406,7 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
         uint8_t* st = smem + s * kStageBytes;
         uint8_t* row_hi = st + row_l * kRowBytes;
 #pragma unroll 1
-        for (int half = 0; half < kBK / 32; ++half) {
+        for (int half = (kEpiWarps == 8 ? cset : 0); half < kBK / 32; half += (kEpiWarps == 8 ? 2 : 1)) {
           uint32_t r[32];
           const int c0 = j * kBK + half * 32;
           tmem_ld_x32(tmem_base + lane_addr + c0, r);
@@ -435,6 +443,7 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
       if (lane == 0) arrive_at_leader(acc1_empty);
 
       // ---- epi2: accumulator 2 -> a2 = leaky(acc * unscale2 + b2eff) -> FC3 -> sigmoid -> probabilities
+      if (cset != 0) continue;   // second column set: back to the next tile's accumulator 1
       mbar_wait(acc2_full, tile_i & 1);
       tc_fence_after();
       const uint32_t t2addr = tmem_base + kAcc2Col + lane_addr;
