@@ -430,6 +430,10 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
 #ifdef ETHCNN_EXP_TIMING
   if (lane < 24) s_conv_phase[warp][lane] = 0;
 #endif
+  // the gate flags of the call are cleared here (the FC kernel, next in the stream, is the first to set them): one launch
+  // less per call than a separate memset
+  if (p.clear_flags != nullptr)
+    for (int i = blockIdx.x * kConvThreads + threadIdx.x; i < p.n_clear_flags; i += gridDim.x * kConvThreads) p.clear_flags[i] = 0u;
   {
     const float4* src = reinterpret_cast<const float4*>(p.convw);
     float4* dst = reinterpret_cast<float4*>(wsm);

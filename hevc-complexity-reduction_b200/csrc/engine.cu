@@ -451,7 +451,9 @@ int run_device(ethcnn_handle* h, DeviceCtx& c, const uint8_t* d_y, int width, in
     }
     d_out = c.gprob;
   }
-  if (gated) CUDA_TRY(cudaMemsetAsync(c.flags, 0, size_t(n_frames) * chunks_per_frame * sizeof(unsigned), stream));
+  // the gate flags are cleared by the first conv launch of the call (mma.sync stage) or by a memset (tcgen05 conv stage)
+  const bool conv_clears_flags = gated && !(h->conv_path == 1 && use_tma);
+  if (gated && !conv_clears_flags) CUDA_TRY(cudaMemsetAsync(c.flags, 0, size_t(n_frames) * chunks_per_frame * sizeof(unsigned), stream));
 
   const float in_scale = (h->mode == ETHCNN_MODE_LDP) ? (10.0f / 255.0f) : (1.0f / 255.0f);
   for (long long begin = 0; begin < total; begin += (long long)c.chunk_ctus) {
@@ -465,6 +467,8 @@ int run_device(ethcnn_handle* h, DeviceCtx& c, const uint8_t* d_y, int width, in
     cl.feat_scale = std::ldexp(1.0f, m->feat_exp);
     c.last_feat_exp = m->feat_exp;
     cl.luma = d_y, cl.pitch = pitch, cl.frame_stride = frame_stride, cl.width = width, cl.height = height;
+    cl.clear_flags = (conv_clears_flags && begin == 0) ? c.flags : nullptr;
+    cl.n_clear_flags = n_frames * chunks_per_frame;
     if (h->conv_path == 1 && use_tma) {   // tensor-core conv stage; needs the TMA tile loader
       ConvTcLaunch tl{};
       tl.blob = m->conv_tc;

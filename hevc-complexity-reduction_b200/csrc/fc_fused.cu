@@ -291,9 +291,14 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
           mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
           uint8_t* st = smem + s * kStageBytes;
           if (lane == 0) {
+#ifdef ETHCNN_EXP_FC_SKIP_ALO   // measurement only (wrong results): a quarter less operand traffic -- is the kernel bound by its L2 feed?
+            if (rank == 0) mbar_arrive_expect_tx(&full[s], kCtas * kABytes);
+            load_tile(st, &map_a_hi, &full[s], ks * kBK, ti.m0);
+#else
             if (rank == 0) mbar_arrive_expect_tx(&full[s], kCtas * 2 * kABytes);
             load_tile(st, &map_a_hi, &full[s], ks * kBK, ti.m0);
             load_tile(st + kABytes, &map_a_lo, &full[s], ks * kBK, ti.m0);
+#endif
           } else if (lane == 1) {
             if (rank == 0) mbar_arrive_expect_tx(&full[s], kCtas * 2 * nb * kRowBytes);
             load_tile(st + 2 * kABytes, wh, &full[s], ks * kBK, nrow);

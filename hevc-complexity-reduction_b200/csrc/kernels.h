@@ -61,6 +61,8 @@ struct ConvLaunch {
   int ctus_per_frame;
   float cst[3];              // S, M, L: input_scale / (256 * pool^2)
   float feat_scale;          // power of two
+  unsigned* clear_flags;     // gate flags to zero before anything downstream sets them (first chunk of a call), or nullptr
+  int n_clear_flags;
   // plain-load tile loader (used when the TMA preconditions do not hold)
   const uint8_t* luma;
   size_t pitch, frame_stride;

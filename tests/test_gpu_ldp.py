@@ -116,3 +116,34 @@ def test_ldp_daemon_file_protocol(eb, ldp_model_dir, tmp_path):
     finally:
         if proc.poll() is None:
             proc.kill()
+
+
+def test_ldp_daemon_fails_fast_without_thresholds_or_checkpoint(eb, ldp_model_dir, tmp_path):
+    """The HM side waits for pred_end.sig without a time-out (TEncGOP.cpp(LDP):1487): a daemon that cannot work must fail at
+    start-up -- like the reference, which dies at import without Thr_info.txt (net_CNN_LSTM_one_step.py:67-68) and at restore
+    without the CNN checkpoint -- not after it has consumed pred_start.sig."""
+    import os
+    import shutil
+
+    d, present = ldp_model_dir
+    # (a) checkpoints present, Thr_info.txt missing
+    a = tmp_path / "no_thr"
+    a.mkdir()
+    for fn in os.listdir(d):
+        if fn != "Thr_info.txt":
+            os.symlink(os.path.realpath(os.path.join(d, fn)), a / fn)
+    open(a / "pred_start.sig", "wb").close()
+    with eb.EthCnn(str(a), None, eb.MODE_LDP, device=0) as net:
+        with pytest.raises(eb.EthCnnError):
+            net.ldp_serve(str(a), max_frames=1, idle_timeout_ms=300)
+    assert (a / "pred_start.sig").exists()          # untouched: nothing was "accepted"
+    # (b) Thr_info.txt present, CNN checkpoint missing
+    b = tmp_path / "no_ckpt"
+    b.mkdir()
+    shutil.copyfile(os.path.join(d, "Thr_info.txt"), b / "Thr_info.txt")
+    open(b / "pred_start.sig", "wb").close()
+    with eb.EthCnn(str(b), None, eb.MODE_LDP, device=0) as net:
+        with pytest.raises(eb.EthCnnError) as e:
+            net.ldp_serve(str(b), max_frames=1, idle_timeout_ms=300)
+        assert e.value.code == -2
+    assert (b / "pred_start.sig").exists()

@@ -168,12 +168,16 @@ def test_full_size_config2_and_config3_frames_vs_oracle(net):
 
 
 @pytest.mark.parametrize("name,W,H,nf,qp,mode", [
+    ("config2-qp22", 1920, 1080, 50, 22, "AI"),   # BASELINE config 2 at full size for each of its four QPs (one checkpoint each):
+    ("config2-qp27", 1920, 1080, 50, 27, "AI"),   # 25 500 CTUs, last CTU row 56 real + 8 zero-padded rows, one gate chunk per frame
+    ("config2-qp32", 1920, 1080, 50, 32, "AI"),
+    ("config2-qp37", 1920, 1080, 50, 37, "AI"),
     ("config3", 4928, 3264, 50, 32, "AI"),     # 196 350 CTUs, 804 MB of luma, sub-batches 1024/1024/1024/855
     ("config4", 2880, 1920, 425, 27, "AI"),    # 573 750 CTUs, 2.35 GB of luma, sub-batches 1024/326, 16 feature chunks
     ("config5", 1920, 1080, 240, 37, "LDP"),   # 122 400 CTUs of residue frames, LDP weights, no gates
 ])
 def test_baseline_full_size_sequences(eb, ai_model_dir, ldp_model_dir, name, W, H, nf, qp, mode):
-    """BASELINE.json configs 3-5 at their full sizes through the host API (pageable source, slabs, feature chunks that
+    """BASELINE.json configs 2-5 at their full sizes through the host API (pageable source, slabs, feature chunks that
     start and end inside frames).  Size-independent properties: the sequence cycles over five base frames, so every
     repetition of a base frame must reproduce its rows bit for bit wherever it falls; rows are probabilities; and the
     first cycle equals the oracle on those five frames (the only part the oracle has to compute)."""

@@ -270,3 +270,38 @@ def test_server_client_protocol_against_a_fake_server(eb, tmp_path):
     f = seen[0].rstrip("\n").split("\t")
     assert f[0] == "PREDICT" and f[1] == os.getcwd() and f[2:] == ["clip.yuv", "1920", "1080", "27", "cu_depth.dat"]
     assert seen[1].split("\t")[2] == "/abs/bad.yuv"
+
+
+def test_corrupt_checkpoint_index_is_rejected_not_read_out_of_bounds(eb, tmp_path):
+    """A crafted .index (huge varints in block handles / entries, negative dims, extents past the data file) must come back as
+    ETHCNN_E_FORMAT from the C++ reader: its bounds checks compare without adding attacker-controlled 64-bit quantities."""
+    import struct
+
+    w = eo.random_weights(5)
+    good = str(tmp_path / "good.dat")
+    tf_bundle.write_bundle(good, w)
+    idx = bytearray(open(good + ".index", "rb").read())
+    data = open(good + ".data-00000-of-00001", "rb").read()
+    lib = eb.load_library()
+
+    def try_index(blob, tag):
+        pre = str(tmp_path / ("bad_%s.dat" % tag))
+        open(pre + ".index", "wb").write(bytes(blob))
+        open(pre + ".data-00000-of-00001", "wb").write(data)
+        rc = lib.ethcnn_debug_pack_model(pre.encode(), C.c_float(1.0), None, None, None, None, None, None, None)
+        assert rc in (-2, -3), (tag, rc)
+
+    huge = b"\xff\xff\xff\xff\xff\xff\xff\xff\xff\x01"                      # varint 2^64 - 1
+    footer = len(idx) - 48
+    try_index(idx[:footer] + huge + huge + huge + huge + bytes(40 - 40) + idx[footer + 40:], "footer_handles")   # offsets wrap
+    f2 = bytearray(idx)
+    f2[footer:footer + 40] = (huge + b"\x04" + b"\x00" + huge)[:40].ljust(40, b"\x00")
+    try_index(f2, "index_handle")
+    # flip bytes inside the data block: crc mismatch or corrupt entries, never a crash
+    rng = np.random.default_rng(1)
+    for trial in range(24):
+        b = bytearray(idx)
+        for pos in rng.integers(0, footer, size=3):
+            b[int(pos)] ^= int(rng.integers(1, 256))
+        try_index(b, "flip%d" % trial)
+    try_index(idx[:20], "truncated")
