@@ -33,6 +33,7 @@
 // fill of out-of-bounds rows/columns IS the reference's zero padding, video_to_cu_depth.py:54-57).
 // One producer warp issues TMA and tabulates the 16x16-pixel block sums of the group (the mean-removal windows of
 // the three branches are 1, 4 and 16 of those blocks); eleven compute warps take warp tasks round-robin.
+#include <cstdlib>
 #include <cstring>
 
 #include "kernels.h"
@@ -430,10 +431,7 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
 #ifdef ETHCNN_EXP_TIMING
   if (lane < 24) s_conv_phase[warp][lane] = 0;
 #endif
-  // the gate flags of the call are cleared here (the FC kernel, next in the stream, is the first to set them): one launch
-  // less per call than a separate memset
-  if (p.clear_flags != nullptr)
-    for (int i = blockIdx.x * kConvThreads + threadIdx.x; i < p.n_clear_flags; i += gridDim.x * kConvThreads) p.clear_flags[i] = 0u;
+  pdl_launch_dependents();   // the FC kernel's CTAs may take over each SM as soon as this CTA leaves it (their prologue overlaps our tail)
   {
     const float4* src = reinterpret_cast<const float4*>(p.convw);
     float4* dst = reinterpret_cast<float4*>(wsm);
@@ -459,6 +457,15 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
     *next_task = 0;
     mbar_fence_init();
   }
+  // Launched as a programmatic dependent of whatever kernel precedes it in the stream (the FC kernel of the previous feature
+  // chunk, the gate kernel of the previous call): the weight copy and barrier set-up above ran while that kernel drained.
+  // Everything below may conflict with it (the flags its gate reads, the feature rows its FC reads, luma a caller's kernel
+  // wrote), so it starts here.
+  pdl_wait();
+  // the gate flags of the call are cleared here (the FC kernel, next in the stream, is the first to set them): one launch
+  // less per call than a separate memset
+  if (p.clear_flags != nullptr)
+    for (int i = blockIdx.x * kConvThreads + threadIdx.x; i < p.n_clear_flags; i += gridDim.x * kConvThreads) p.clear_flags[i] = 0u;
   __syncthreads();
 
   const int n_groups = (p.n_ctus + kGroupCtus - 1) / kGroupCtus;
@@ -641,14 +648,16 @@ cudaError_t launch_conv_features(const CUtensorMap* tmap, const ConvLaunch& p, i
   if (p.n_ctus <= 0) return cudaSuccess;
   const int n_groups = (p.n_ctus + kGroupCtus - 1) / kGroupCtus;
   const int grid = n_groups < sm_count ? n_groups : sm_count;
-  if (tmap) {
-    conv_features_kernel<true><<<grid, kConvThreads, kConvSmemBytes, stream>>>(*tmap, p);
-  } else {
-    CUtensorMap dummy;
-    memset(&dummy, 0, sizeof(dummy));
-    conv_features_kernel<false><<<grid, kConvThreads, kConvSmemBytes, stream>>>(dummy, p);
-  }
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kConvThreads), cfg.dynamicSmemBytes = kConvSmemBytes, cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = getenv("ETHCNN_NO_PDL") ? 0 : 1;   // measurement switch
+  if (tmap) return cudaLaunchKernelEx(&cfg, conv_features_kernel<true>, *tmap, p);
+  CUtensorMap dummy;
+  memset(&dummy, 0, sizeof(dummy));
+  return cudaLaunchKernelEx(&cfg, conv_features_kernel<false>, dummy, p);
 }
 
 // ---------------------------------------------------------------------------------------------------

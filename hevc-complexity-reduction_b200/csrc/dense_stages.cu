@@ -3,7 +3,10 @@
 //   HEADS : net_CNN.py:158-163,168-173,180-185   a2 = leaky([a1,q] W2 + b2); y = sigmoid([a2,q] W3 + b3)
 //   GATE  : net_CNN.py:175,187 over each <=1024-CTU sub-batch of one frame (video_to_cu_depth.py:64-70)
 //   decisions: TLibEncoder/TEncCu.cpp:448-462
+#include <cstdlib>
+
 #include "kernels.h"
+#include "ptx_sm100.cuh"
 
 namespace ethcnn {
 namespace {
@@ -176,6 +179,7 @@ __global__ void __launch_bounds__(192) heads_kernel(const HeadsLaunch p) {
 // When g1 is false the gated y32 is all zeros, so g2 = (0 > t2).
 __global__ void gate_kernel(float* __restrict__ prob, const unsigned* __restrict__ flags, float t2, int ctus_per_frame,
                             int chunks_per_frame) {
+  pdl_wait();   // launched as a programmatic dependent of the FC kernel: its rows and flags are complete from here on
   // one block per (frame, sub-batch); almost always both gates are open and the block has nothing to do
   const int f = blockIdx.x / chunks_per_frame, ch = blockIdx.x - f * chunks_per_frame;
   const unsigned fl = flags[blockIdx.x];
@@ -298,8 +302,13 @@ cudaError_t launch_gate(float* prob, const unsigned* flags, float t2, long long 
                         int chunks_per_frame, cudaStream_t stream) {
   if (n_total <= 0) return cudaSuccess;
   const long long n_frames = n_total / ctus_per_frame;   // a call always covers whole frames
-  gate_kernel<<<unsigned(n_frames * chunks_per_frame), 256, 0, stream>>>(prob, flags, t2, ctus_per_frame, chunks_per_frame);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(unsigned(n_frames * chunks_per_frame)), cfg.blockDim = dim3(256), cfg.dynamicSmemBytes = 0, cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = getenv("ETHCNN_NO_PDL") ? 0 : 1;   // measurement switch
+  return cudaLaunchKernelEx(&cfg, gate_kernel, prob, flags, t2, ctus_per_frame, chunks_per_frame);
 }
 
 cudaError_t launch_gate_export(const float* src, float* dst, const unsigned* flags, float t2, long long n_total,

@@ -118,6 +118,7 @@ struct DeviceCtx {
   std::vector<void*> peer_owned;  // gather buffers this device exported (ethcnn_peer_buffer_create)
   std::vector<void*> peer_opened; // peer buffers mapped into this process (ethcnn_peer_buffer_open)
   cudaEvent_t ev_last = nullptr;  // end of the previous device call (scratch reuse across streams)
+  cudaStream_t last_stream = nullptr;
   // staging for the host path
   static constexpr int kSlabs = 3;
   uint8_t* d_slab[kSlabs] = {};
@@ -431,7 +432,10 @@ int run_device(ethcnn_handle* h, DeviceCtx& c, const uint8_t* d_y, int width, in
   const long long total = (long long)n_frames * ctus_per_frame;
   if (total > 0x7fffffffLL / 32) return fail(ETHCNN_E_ARG, "too many CTUs in one call; split the sequence");
   if ((rc = ensure_scratch(h, c, size_t(n_frames) * chunks_per_frame))) return rc;
-  if (c.ev_last) CUDA_TRY(cudaStreamWaitEvent(stream, c.ev_last, 0));
+  // scratch reuse across streams: order this call behind the previous one unless it is on the same stream anyway (then the
+  // wait would only stand between the previous call's gate kernel and this call's programmatically dependent conv kernel)
+  if (c.ev_last && stream != c.last_stream) CUDA_TRY(cudaStreamWaitEvent(stream, c.ev_last, 0));
+  c.last_stream = stream;
 
   CUtensorMap tmap;
   const char* terr = nullptr;

@@ -24,6 +24,8 @@
 #include <cstring>
 
 #include "fc_fused.h"
+#include <cstdlib>
+
 #include "kernels.h"
 #include "ptx_sm100.cuh"
 
@@ -236,6 +238,7 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  pdl_launch_dependents();   // the gate kernel may be scheduled behind us; it waits for our completion itself
   for (int i = threadIdx.x; i < kW3Floats; i += kThreads) w3s[i] = p.w3[i];
   for (int i = threadIdx.x; i < 336; i += kThreads) b2s[i] = p.b2eff[i];
   if (threadIdx.x < 21) b3s[threadIdx.x] = p.b3eff[threadIdx.x];
@@ -262,6 +265,9 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
   if (kCtas == 2) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform: feeds the MMA's uniform registers
+  // Everything above (tables, barriers, tensor memory) touched only weights and this CTA's own state: when launched as a
+  // programmatic dependent of the conv kernel it ran while that kernel was finishing.  The features are read below.
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer ------------------------------------------------
@@ -626,10 +632,18 @@ cudaError_t launch_fc_fused(const __half* feat_hi, const __half* feat_lo, const 
     fc_fused_kernel<<<units, kThreads, Geo<1>::kSmemBytes, stream>>>(map_a_hi, map_a_lo, m.w1_hi_t0, m.w1_lo_t0, m.w1_hi_t1, m.w1_lo_t1,
                                                                     m.w2_hi[0], m.w2_lo[0], m.w2_hi[1], m.w2_lo[1], m.w2_hi[2], m.w2_lo[2],
                                                                     p, m_blocks);
-  else
-    fc_fused_pair_kernel<<<2 * units, kThreads, Geo<2>::kSmemBytes, stream>>>(map_a_hi, map_a_lo, m.w1_hi_t0, m.w1_lo_t0, m.w1_hi_t1,
-                                                                            m.w1_lo_t1, m.w2_hi[0], m.w2_lo[0], m.w2_hi[1], m.w2_lo[1],
-                                                                            m.w2_hi[2], m.w2_lo[2], p, m_blocks);
+  else {
+    // programmatic dependent launch: the CTAs start (prologue only, see pdl_wait in the kernel) while the conv kernel ahead of
+    // us in the stream drains
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * units), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = Geo<2>::kSmemBytes, cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = getenv("ETHCNN_NO_PDL") ? 0 : 1;   // measurement switch
+    return cudaLaunchKernelEx(&cfg, fc_fused_pair_kernel, map_a_hi, map_a_lo, m.w1_hi_t0, m.w1_lo_t0, m.w1_hi_t1, m.w1_lo_t1, m.w2_hi[0],
+                              m.w2_lo[0], m.w2_hi[1], m.w2_lo[1], m.w2_hi[2], m.w2_lo[2], p, m_blocks);
+  }
   return cudaGetLastError();
 }
 

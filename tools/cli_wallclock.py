@@ -13,14 +13,13 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import assets  # noqa: E402
-from oracle import ethcnn_oracle as eo  # noqa: E402
+from tools import synth  # noqa: E402
 
 PKG = os.path.join(ROOT, "hevc-complexity-reduction_b200")
 
 
 def make_file(path, W, H, nf):
-    base = [eo.synth_frame(W, H, 500 + k) for k in range(5)]
+    base = [synth.synth_frame(W, H, 500 + k) for k in range(5)]
     uv = bytes([128]) * (W * H // 2)
     with open(path, "wb") as f:
         for k in range(nf):
@@ -29,11 +28,19 @@ def make_file(path, W, H, nf):
 
 
 def main():
+    import argparse
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", default="config1,config2,config3")
+    ap.add_argument("--skip-inprocess", action="store_true", help="only the resident-server clients (ETHCNN_GPUS applies to the server)")
+    args = ap.parse_args()
     work = tempfile.mkdtemp(prefix="cli_wall_")
-    assets.materialize(work, "AI")
+    synth.prepare_models(work)
     os.symlink(os.path.join(PKG, "video_to_cu_depth.py"), os.path.join(work, "video_to_cu_depth.py"))   # as INTEGRATION.md says
     env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + PKG)
-    cases = (("config1", 768, 512, 1, 32), ("config2", 1920, 1080, 50, 32), ("config3", 4928, 3264, 50, 32))
+    cases = [c for c in (("config1", 768, 512, 1, 32), ("config2", 1920, 1080, 50, 32), ("config3", 4928, 3264, 50, 32),
+                         ("config4", 2880, 1920, 425, 27)) if c[0] in args.cases.split(",")]
+    print("ETHCNN_GPUS = %s" % os.environ.get("ETHCNN_GPUS", "1"))
     # a resident server (video_to_cu_depth --serve): the clients below hand their request to it
     sock = os.path.join(work, "ethcnn.sock")
     srv = subprocess.Popen([os.path.join(PKG, "bin", "video_to_cu_depth"), "--serve", sock], cwd=work, stderr=subprocess.DEVNULL)
@@ -49,7 +56,8 @@ def main():
         n = nf * r * c
         py = [sys.executable, "video_to_cu_depth.py", yuv, str(W), str(H), str(qp)]
         cc = [os.path.join(PKG, "bin", "video_to_cu_depth"), yuv, str(W), str(H), str(qp)]
-        for label, cmd, run_env in (("python shim", py, env), ("C++ CLI", cc, env), ("shim->server", py, env_srv), ("CLI->server", cc, env_srv)):
+        runs = (("python shim", py, env), ("C++ CLI", cc, env), ("shim->server", py, env_srv), ("CLI->server", cc, env_srv))
+        for label, cmd, run_env in (runs[2:] if args.skip_inprocess else runs):
             times = []
             for _ in range(3):
                 out = os.path.join(work, "cu_depth.dat")
