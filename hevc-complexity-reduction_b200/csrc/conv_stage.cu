@@ -141,9 +141,25 @@ __device__ __forceinline__ uint32_t centred_half2(uint32_t biased_bits, float ce
 // (y = 8T + 4 ph + d/2 + 2 ki, x = 8 rx + 4 pl + 2 (d%2) + {0,1}) as s - 128 pool^2, s = integer sum of the pool x pool
 // pixels: an integer of magnitude <= 2048, i.e. EXACT in fp16 -- conv1 needs no lo part for its A operand, and the mean
 // removal (a per-window constant) moves into the bias: conv(s - mean) = conv(s - centre) + (centre - mean) * sum(taps).
+// xs[c] = v[c ^ m] for m in 0..3 (two conditional swaps, eight selects)
+__device__ __forceinline__ void unpermute4(const uint32_t (&v)[4], int m, uint32_t (&xs)[4]) {
+  const bool b0 = m & 1, b1 = m & 2;
+  const uint32_t w0 = b0 ? v[1] : v[0], w1 = b0 ? v[0] : v[1], w2 = b0 ? v[3] : v[2], w3 = b0 ? v[2] : v[3];
+  xs[0] = b1 ? w2 : w0, xs[1] = b1 ? w3 : w1, xs[2] = b1 ? w0 : w2, xs[3] = b1 ? w1 : w3;
+}
+
 template <int P>
-__device__ __forceinline__ void load_x_p(uint32_t blk, int T, int d, uint32_t (&xh)[16]) {
+__device__ __forceinline__ void load_x_p(uint32_t blk, int T, int lane, uint32_t (&xh)[16]) {
+  const int d = lane & 3, g = lane >> 2;
   const int ky0 = d >> 1, e = d & 1;
+  // Pooled branches: the eight lane groups of a warp read the same offsets of DIFFERENT tiles / quads, i.e. the same banks
+  // (tile stride 4096 B; TMA wants 128-byte aligned tiles, so the tiles cannot be skewed): 16 wavefronts per LDS.64 in the L task,
+  // 4 per LDS.32 in the M tasks (profiles/r02h_conv.md: 37 % of all shared-memory wavefronts were conflicts, 70 % of them from the
+  // L task).  Each group therefore walks its four (pl, rx) elements of a row pair in its own order (index c ^ m) and, for the 4x4
+  // pooling, its four pixel rows starting at its own parity -- sums are order-independent -- and the elements are put back
+  // in place with selects: M conflict-free, L 4 wavefronts instead of 16.
+  const int m = P == 2 ? ((g >> 1) & 3) : (g & 3);
+  const int apar = (g >> 2) & 1;
 #pragma unroll
   for (int ph = 0; ph < 2; ++ph)
 #pragma unroll
@@ -159,42 +175,43 @@ __device__ __forceinline__ void load_x_p(uint32_t blk, int T, int d, uint32_t (&
           for (int rx = 0; rx < 2; ++rx)
             xh[4 * (2 * ph + pl) + rx + 2 * ki] = centred_half2(__byte_perm(w[2 * rx + pl], 0x64646464u, sel), 1024.f + 128.f);
       } else {
+        uint32_t v[4], xs[4];
 #pragma unroll
-        for (int pl = 0; pl < 2; ++pl)
+        for (int c = 0; c < 4; ++c) {
+          const int cc = c ^ m;                               // this group's element (pl, rx) = (cc / 2, cc % 2) at step c
+          const int x0 = 8 * (cc & 1) + 4 * (cc >> 1) + 2 * e;
+          if (P == 2) {
+            // the two pixel rows in lane-dependent order (the sum is symmetric): lanes d/2 = 0, 1 hit different banks
+            const uint32_t a = lds_u32(blk + (2 * y + ky0) * kCtu + 2 * x0), b = lds_u32(blk + (2 * y + (ky0 ^ 1)) * kCtu + 2 * x0);
+            const uint32_t s0 = __dp4a(b, 0x00000101u, __dp4a(a, 0x00000101u, 0x6400u));   // 0x6400 + s: fp16 bits of 1024 + s
+            const uint32_t s1 = __dp4a(b, 0x01010000u, __dp4a(a, 0x01010000u, 0x6400u));
+            v[c] = centred_half2(__byte_perm(s0, s1, 0x5410u), 1024.f + 512.f);
+          } else {
+            uint32_t s0 = 0u - 2048u, s1 = 0u - 2048u;
 #pragma unroll
-          for (int rx = 0; rx < 2; ++rx) {
-            const int x0 = 8 * rx + 4 * pl + 2 * e;
-            uint32_t v;
-            if (P == 2) {
-              // the two pixel rows in lane-dependent order (the sum is symmetric): lanes d/2 = 0, 1 hit different banks
-              const uint32_t a = lds_u32(blk + (2 * y + ky0) * kCtu + 2 * x0), b = lds_u32(blk + (2 * y + (ky0 ^ 1)) * kCtu + 2 * x0);
-              const uint32_t s0 = __dp4a(b, 0x00000101u, __dp4a(a, 0x00000101u, 0x6400u));   // 0x6400 + s: fp16 bits of 1024 + s
-              const uint32_t s1 = __dp4a(b, 0x01010000u, __dp4a(a, 0x01010000u, 0x6400u));
-              v = centred_half2(__byte_perm(s0, s1, 0x5410u), 1024.f + 512.f);
-            } else {
-              uint32_t s0 = 0u - 2048u, s1 = 0u - 2048u;
-#pragma unroll
-              for (int a = 0; a < 4; ++a) {
-                const uint2 q = lds_u64(blk + (4 * y + a) * kCtu + 4 * x0);
-                s0 = __dp4a(q.x, 0x01010101u, s0);
-                s1 = __dp4a(q.y, 0x01010101u, s1);
-              }
-              const __half2 h = __floats2half2_rn(__int2float_rn(int(s0)), __int2float_rn(int(s1)));
-              v = *reinterpret_cast<const uint32_t*>(&h);
+            for (int a = 0; a < 4; ++a) {
+              const uint2 q = lds_u64(blk + (4 * y + (a ^ apar)) * kCtu + 4 * x0);
+              s0 = __dp4a(q.x, 0x01010101u, s0);
+              s1 = __dp4a(q.y, 0x01010101u, s1);
             }
-            xh[4 * (2 * ph + pl) + rx + 2 * ki] = v;
+            const __half2 h = __floats2half2_rn(__int2float_rn(int(s0)), __int2float_rn(int(s1)));
+            v[c] = *reinterpret_cast<const uint32_t*>(&h);
           }
+        }
+        unpermute4(v, m, xs);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) xh[4 * (2 * ph + (c >> 1)) + (c & 1) + 2 * ki] = xs[c];
       }
     }
 }
 
-__device__ __forceinline__ void load_x(int pool, uint32_t blk, int T, int d, uint32_t (&xh)[16]) {
+__device__ __forceinline__ void load_x(int pool, uint32_t blk, int T, int lane, uint32_t (&xh)[16]) {
   if (pool == 1) {
-    load_x_p<1>(blk, T, d, xh);
+    load_x_p<1>(blk, T, lane, xh);
   } else if (pool == 2) {
-    load_x_p<2>(blk, T, d, xh);
+    load_x_p<2>(blk, T, lane, xh);
   } else {
-    load_x_p<4>(blk, T, d, xh);
+    load_x_p<4>(blk, T, lane, xh);
   }
 }
 
@@ -312,7 +329,7 @@ __device__ __forceinline__ void warp_task(const int pool, const uint32_t wb, con
     const float2 be_lo = st ? bb_lo : ba_lo, be_hi = st ? bb_hi : ba_hi;
     PH_MARK(phb, 0);   // task set-up / window sums
     uint32_t xh[16];
-    load_x(pool, blk, T, d, xh);
+    load_x(pool, blk, T, lane, xh);
     PH_MARK(phb, 1);   // pixel loads + conversion
     float d2[3][4];
 #pragma unroll
