@@ -81,31 +81,6 @@ __device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ah)[4], con
   mma16816(d, al, bh);
 }
 
-// Packed fp32 pair arithmetic (sm_100 FFMA2 / FMUL2 / FADD2): the accumulator pairs of an mma.sync C fragment sit in
-// adjacent registers, so bias, leaky and the hi/lo split are done two values at a time.
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
-  float2 r;
-  asm("{\n.reg .b64 ra, rb, rc, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmov.b64 rc, {%6, %7};\n"
-      "fma.rn.f32x2 rd, ra, rb, rc;\nmov.b64 {%0, %1}, rd;\n}"
-      : "=f"(r.x), "=f"(r.y)
-      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-  return r;
-}
-__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
-  float2 r;
-  asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmul.rn.f32x2 rd, ra, rb;\nmov.b64 {%0, %1}, rd;\n}"
-      : "=f"(r.x), "=f"(r.y)
-      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-  return r;
-}
-__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
-  float2 r;
-  asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nsub.rn.f32x2 rd, ra, rb;\nmov.b64 {%0, %1}, rd;\n}"
-      : "=f"(r.x), "=f"(r.y)
-      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-  return r;
-}
-
 // One accumulator pair -> leaky(d * u + b) -> packed fp16 hi pair and lo pair with hi + lo == value to ~22 bits.
 __device__ __forceinline__ void act_split(float d0, float d1, float2 u, float2 b, uint32_t& hi, uint32_t& lo) {
 #ifdef ETHCNN_EXP_NO_ACT    // measurement only: the MMA skeleton without the fragment epilogues

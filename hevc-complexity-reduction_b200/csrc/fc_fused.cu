@@ -145,6 +145,21 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[32]) {
 __device__ __forceinline__ float leaky(float v) { return fmaxf(0.2f * v, v); }
 __device__ __forceinline__ float sigmoidf(float v) { return 1.0f / (1.0f + expf(-v)); }
 
+#ifdef ETHCNN_EXP_FC_TIMING   // measurement only: where the MMA issuer (leader CTA) spends its cycles
+__device__ unsigned long long g_fc_issuer[8];
+__device__ unsigned long long g_fc_epi[8];
+#define FCT_BEGIN() long long fct_t = clock64()
+#define FCT_MARK(k)                                                              \
+  do {                                                                           \
+    const long long fct_n = clock64();                                           \
+    if (lane == 0) fct_acc[k] += (unsigned long long)(fct_n - fct_t);            \
+    fct_t = fct_n;                                                               \
+  } while (0)
+#else
+#define FCT_BEGIN()
+#define FCT_MARK(k)
+#endif
+
 struct TileInfo {
   int type;      // 1 = head 16, 0 = heads 64 + 32
   int m0;        // first CTU row of the tile
@@ -224,7 +239,11 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
   // cluster addresses of the leader's copies (identical shared-memory layout in both CTAs)
   auto at_leader = [&](uint64_t* bar) -> uint32_t { return kCtas == 2 ? mapa_shared(smem_u32(bar), 0) : smem_u32(bar); };
   auto arrive_at_leader = [&](uint64_t* bar) {
+#ifdef ETHCNN_FC_CLUSTER_RELEASE   // the round-1 form: every hand-off with a cluster-scope release
     if (kCtas == 2) mbar_arrive_remote(mapa_shared(smem_u32(bar), 0));
+#else
+    if (kCtas == 2) mbar_arrive_remote_relaxed_scope(mapa_shared(smem_u32(bar), 0));
+#endif
     else mbar_arrive(bar);
   };
   auto wait_shared = [&](uint64_t* bar, uint32_t parity) {   // a leader barrier both CTAs arrive on
@@ -242,7 +261,8 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
   for (int i = threadIdx.x; i < kW3Floats; i += kThreads) w3s[i] = p.w3[i];
   for (int i = threadIdx.x; i < 336; i += kThreads) b2s[i] = p.b2eff[i];
   if (threadIdx.x < 21) b3s[threadIdx.x] = p.b3eff[threadIdx.x];
-  for (int i = threadIdx.x; i < kFc1; i += kThreads) b1s[i] = p.b1[i];
+  // b1 pre-scaled by 2^a1_exp: leaky(acc u + b) 2^e == leaky(acc (u 2^e) + b 2^e) exactly, one multiply less per activation
+  for (int i = threadIdx.x; i < kFc1; i += kThreads) b1s[i] = p.b1[i] * p.a1_scale;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a_hi), prefetch_tmap(&map_a_lo);
@@ -336,15 +356,21 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer (the leader CTA of a pair only) -------------------------
     int it = 0, tile_i = 0, a2_cnt[kStages] = {};
+#ifdef ETHCNN_EXP_FC_TIMING
+    unsigned long long fct_acc[8] = {};
+#endif
+    FCT_BEGIN();
     for (int t; rank == 0 && (t = tile_of(unit, tile_i, n_units, m_blocks)) >= 0; ++tile_i) {
       const TileInfo ti = decode_tile(t, kBM * kCtas, row_ofs);
       const int nb = ti.n1 / kCtas;
       wait_shared(acc1_empty, (tile_i & 1) ^ 1);
+      FCT_MARK(0);   // waiting for accumulator 1 to be drained
       tc_fence_after();
       const uint32_t idesc1 = idesc_f16<kCtas>(ti.n1);
       for (int ks = 0; ks < kKSteps; ++ks, ++it) {
         const int s = it % kStages;
         mbar_wait(&full[s], (it / kStages) & 1);
+        FCT_MARK(1);   // FC1: waiting for the operands of the stage
         tc_fence_after();
         __syncwarp();
         {   // all lanes, converged; one elected lane issues (see umma_f16)
@@ -362,9 +388,11 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
           if (ks == kKSteps - 1) umma_commit<kCtas>(acc1_full);
         }
         __syncwarp();
+        FCT_MARK(2);   // FC1: issuing
       }
       // FC2: A operand = this tile's a1 slices written by the epilogue warps into the ring
       wait_shared(acc2_empty, (tile_i & 1) ^ 1);
+      FCT_MARK(3);   // waiting for accumulator 2 of the previous tile to be drained
       tc_fence_after();
       for (int j = 0; j < ti.nslices; ++j, ++it) {
         const int s = it % kStages;
@@ -373,6 +401,7 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
         mbar_wait(&full[s], (it / kStages) & 1);
         wait_shared(&a2_full[s], a2_cnt[s] & 1);
         ++a2_cnt[s];
+        FCT_MARK(4);   // FC2: waiting for W2 and the a1 slice from the epilogue warps
         tc_fence_after();
         __syncwarp();
         {
@@ -392,8 +421,14 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
           if (j == ti.nslices - 1) umma_commit<kCtas>(acc2_full);
         }
         __syncwarp();
+        FCT_MARK(5);   // FC2: issuing
       }
     }
+#ifdef ETHCNN_EXP_FC_TIMING
+    if (lane == 0 && rank == 0)
+      for (int k = 0; k < 6; ++k) atomicAdd(&g_fc_issuer[k], fct_acc[k]);
+    if (lane == 0 && rank == 0) atomicAdd(&g_fc_issuer[6], 1ull);
+#endif
   } else {
     // ------------------------------------------------ epilogue warps ------------------------------------------------
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
@@ -403,6 +438,10 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
     const int row_l = q * 32 + lane;        // row inside the tile = TMEM lane
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     int it = 0, tile_i = 0;
+#ifdef ETHCNN_EXP_FC_TIMING
+    unsigned long long fct_acc[8] = {};
+#endif
+    FCT_BEGIN();
     for (int t; (t = tile_of(unit, tile_i, n_units, m_blocks)) >= 0; ++tile_i) {
       const TileInfo ti = decode_tile(t, kBM * kCtas, row_ofs);
       const int row = ti.m0 + row_l;
@@ -410,10 +449,12 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
       it += kKSteps;
       // ---- epi1: accumulator 1 -> a1 = leaky(acc * unscale1 + b1) -> fp16 hi/lo slices in the ring (FC2 A operand)
       mbar_wait(acc1_full, tile_i & 1);
+      FCT_MARK(0);   // epilogue: waiting for accumulator 1 (includes epi2 of the previous tile)
       tc_fence_after();
       for (int j = 0; j < ti.nslices; ++j, ++it) {
         const int s = it % kStages;
         mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);   // the MMAs that last read this stage have retired
+        FCT_MARK(1);   // epi1: waiting for the ring stage
         uint8_t* st = smem + s * kStageBytes;
         uint8_t* row_hi = st + row_l * kRowBytes;
 #pragma unroll 1
@@ -421,22 +462,34 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
           uint32_t r[32];
           const int c0 = j * kBK + half * 32;
           tmem_ld_x32(tmem_base + lane_addr + c0, r);
-          float a[32];
+          // a1 * 2^a1_exp = leaky(acc * (unscale1 2^a1_exp) + b1 2^a1_exp) on packed fp32 pairs (FFMA2 / FMUL2), then the exact
+          // fp16 hi / lo split: 4.5 instructions per activation (the drain sits on the tensor pipe's critical path)
+          const float us = p.unscale1 * p.a1_scale;
+          float2 a[16];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) a[i] = leaky(fmaf(__uint_as_float(r[i]), p.unscale1, b1s[ti.n0 + c0 + i]));
+          for (int i = 0; i < 16; i += 2) {
+            const float4 b = *reinterpret_cast<const float4*>(b1s + ti.n0 + c0 + 2 * i);
+            const float2 t0 = fma2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), make_float2(us, us), make_float2(b.x, b.y));
+            const float2 t1 = fma2(make_float2(__uint_as_float(r[2 * i + 2]), __uint_as_float(r[2 * i + 3])), make_float2(us, us), make_float2(b.z, b.w));
+            const float2 m0 = mul2(t0, make_float2(0.2f, 0.2f)), m1 = mul2(t1, make_float2(0.2f, 0.2f));
+            a[i] = make_float2(fmaxf(m0.x, t0.x), fmaxf(m0.y, t0.y));
+            a[i + 1] = make_float2(fmaxf(m1.x, t1.x), fmaxf(m1.y, t1.y));
+          }
           if (p.fc1_out != nullptr && live) {
+            const float inv = 1.0f / p.a1_scale;   // a power of two: exact
             float4* o = reinterpret_cast<float4*>(p.fc1_out + size_t(row) * kFc1 + ti.n0 + c0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+            for (int i = 0; i < 8; ++i) o[i] = make_float4(a[2 * i].x * inv, a[2 * i].y * inv, a[2 * i + 1].x * inv, a[2 * i + 1].y * inv);
           }
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {     // 16-byte chunks of 8 fp16; swizzle: chunk ^= row % 8 (128 B) | (row / 2) % 4 (64 B)
             uint32_t hw[4], lw[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float s0 = a[8 * cc + 2 * e] * p.a1_scale, s1 = a[8 * cc + 2 * e + 1] * p.a1_scale;
-              const __half2 h = __floats2half2_rn(s0, s1);
-              const __half2 l = __floats2half2_rn(s0 - __low2float(h), s1 - __high2float(h));
+              const float2 v = a[4 * cc + e];
+              const __half2 h = __floats2half2_rn(v.x, v.y);
+              const float2 lf = sub2(v, make_float2(__low2float(h), __high2float(h)));
+              const __half2 l = __floats2half2_rn(lf.x, lf.y);
               hw[e] = *reinterpret_cast<const uint32_t*>(&h);
               lw[e] = *reinterpret_cast<const uint32_t*>(&l);
             }
@@ -445,9 +498,11 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
             *reinterpret_cast<uint4*>(row_hi + kABytes + chunk) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
           }
         }
+        FCT_MARK(2);   // epi1: tcgen05.ld + math + st.shared
         asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes -> visible to the MMA (async proxy)
         __syncwarp();
         if (lane == 0) arrive_at_leader(&a2_full[s]);
+        FCT_MARK(3);   // epi1: fence + arrive
       }
       tc_fence_before();
       __syncwarp();
@@ -529,7 +584,14 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) arrive_at_leader(acc2_empty);
+      FCT_MARK(4);   // epi2
     }
+#ifdef ETHCNN_EXP_FC_TIMING
+    if (lane == 0 && rank == 0 && warp == 2) {
+      for (int k = 0; k < 5; ++k) atomicAdd(&g_fc_epi[k], fct_acc[k]);
+      atomicAdd(&g_fc_epi[6], 1ull);
+    }
+#endif
   }
 
   tc_fence_before();
@@ -587,6 +649,23 @@ bool make_kmajor_map(CUtensorMap* map, const __half* base, uint64_t k_len, uint6
 }
 
 }  // namespace
+
+#ifdef ETHCNN_EXP_FC_TIMING
+}  // namespace ethcnn
+extern "C" int ethcnn_debug_fc_issuer(unsigned long long* out8, int reset) {
+  unsigned long long z[8] = {};
+  if (cudaMemcpyFromSymbol(out8, ethcnn::g_fc_issuer, sizeof(z)) != cudaSuccess) return -1;
+  if (reset && cudaMemcpyToSymbol(ethcnn::g_fc_issuer, z, sizeof(z)) != cudaSuccess) return -1;
+  return 0;
+}
+extern "C" int ethcnn_debug_fc_epi(unsigned long long* out8, int reset) {
+  unsigned long long z[8] = {};
+  if (cudaMemcpyFromSymbol(out8, ethcnn::g_fc_epi, sizeof(z)) != cudaSuccess) return -1;
+  if (reset && cudaMemcpyToSymbol(ethcnn::g_fc_epi, z, sizeof(z)) != cudaSuccess) return -1;
+  return 0;
+}
+namespace ethcnn {
+#endif
 
 bool fc_fused_prepare_weights(const __half* w1_hi, const __half* w1_lo, const __half* const w2_hi[3],
                               const __half* const w2_lo[3], FusedWeights* out, const char** err) {

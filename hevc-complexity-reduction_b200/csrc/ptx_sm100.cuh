@@ -66,6 +66,13 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t cta_addr, uint32_t rank
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// The same arrive with the default (.release.cta) semantics.  For hand-offs whose consumer is NOT a generic-proxy load in
+// another CTA: data written to shared memory for the tensor core (made visible to the async proxy by fence.proxy.async) or
+// tensor memory that has been drained (tcgen05.fence::before_thread_sync).  A cluster-scope release costs ~1 600 cycles per
+// arrive here (it flushes through L1), measured on the epilogue warps of the fused FC kernel.
+__device__ __forceinline__ void mbar_arrive_remote_relaxed_scope(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -128,6 +135,31 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
 // no-ops for a normally launched kernel.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Packed fp32 pair arithmetic (sm_100 FFMA2 / FMUL2 / FADD2): the accumulator pairs of an mma.sync C fragment sit in
+// adjacent registers, so bias, leaky and the hi/lo split are done two values at a time.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("{\n.reg .b64 ra, rb, rc, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmov.b64 rc, {%6, %7};\n"
+      "fma.rn.f32x2 rd, ra, rb, rc;\nmov.b64 {%0, %1}, rd;\n}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 r;
+  asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmul.rn.f32x2 rd, ra, rb;\nmov.b64 {%0, %1}, rd;\n}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  float2 r;
+  asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nsub.rn.f32x2 rd, ra, rb;\nmov.b64 {%0, %1}, rd;\n}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

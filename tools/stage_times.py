@@ -82,6 +82,20 @@ def main():
             names = ("setup", "load_x", "conv1+act+conv2", "act2+stores", "conv3", "act3+stores", "wait_tiles", "-")
             res["conv_phase_cycles_per_ctu"] = {br: {names[k]: round(buf[8 * b + k] / res["ctus"], 1) for k in range(7)}
                                                 for b, br in enumerate(("S", "M", "L"))}
+        if hasattr(lib, "ethcnn_debug_fc_issuer"):     # -DETHCNN_EXP_FC_TIMING: where the MMA issuer of the fused FC kernel waits
+            import ctypes as C
+            b8 = (C.c_ulonglong * 8)()
+            e8 = (C.c_ulonglong * 8)()
+            lib.ethcnn_debug_fc_issuer(b8, 1)
+            lib.ethcnn_debug_fc_epi(e8, 1)
+            net.predict_luma_device(dl.data_ptr(), W, H, W, W * H, nf, args.qp, out.data_ptr(), s.cuda_stream)
+            torch.cuda.synchronize()
+            lib.ethcnn_debug_fc_issuer(b8, 0)
+            lib.ethcnn_debug_fc_epi(e8, 0)
+            en = ("wait_acc1_full", "epi1_wait_stage", "epi1_ld_math_store", "epi1_fence_arrive", "epi2")
+            res["fc_epilogue_warp_cycles_per_leader_cta"] = {en[k]: round(e8[k] / max(1, e8[6])) for k in range(5)}
+            nm = ("wait_acc1_empty", "fc1_wait_operands", "fc1_issue", "wait_acc2_empty", "fc2_wait", "fc2_issue")
+            res["fc_issuer_cycles_per_leader_cta"] = {nm[k]: round(b8[k] / max(1, b8[6])) for k in range(6)}
     print(json.dumps(res))
 
 
