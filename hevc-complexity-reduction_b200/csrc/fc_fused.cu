@@ -104,6 +104,37 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint6
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// The same with the A operand in TENSOR MEMORY (lane = row, every 32-bit column two consecutive K elements, low half first).
+template <int kCtas>
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  if (kCtas == 1)
+    asm volatile(
+        "{\n.reg .pred p, e;\n.reg .b32 rx;\nelect.sync rx|e, 0xffffffff;\nsetp.ne.b32 p, %4, 0;\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n.reg .pred p, e;\n.reg .b32 rx;\nelect.sync rx|e, 0xffffffff;\nsetp.ne.b32 p, %4, 0;\n"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+// FC2's A operand: 1 = the epilogue warps write a1 (fp16 hi / lo) back into the tensor-memory columns they just drained and the
+// FC2 MMAs read it from there (TS mode): no shared-memory stores, no generic->async proxy fence (~1 000 cycles per slice on the
+// tensor pipe's critical path), no ring stage to wait for.  0 = through the shared-memory ring (round 1).
+#ifndef ETHCNN_FC_A2_TMEM
+#define ETHCNN_FC_A2_TMEM (ETHCNN_FC_BK == 64)
+#endif
+constexpr bool kA2Tmem = ETHCNN_FC_A2_TMEM;
+
 // Arrive on `bar` when all MMAs issued so far by the elected lane have retired; for a pair, on that barrier in BOTH CTAs.
 // (elect.sync returns the same lane every time for a full mask, so the commit tracks the MMAs above.)
 template <int kCtas>
@@ -413,9 +444,17 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             const uint64_t adv = uint64_t(k * 32 >> 4);
-            umma_f16<kCtas>(d2, da_hi + adv, db_hi + adv, idesc2, (first && k == 0) ? 0u : 1u);
-            umma_f16<kCtas>(d2, da_hi + adv, db_lo + adv, idesc2, 1);
-            umma_f16<kCtas>(d2, da_lo + adv, db_hi + adv, idesc2, 1);
+            if (kA2Tmem) {
+              // a1 of K elements [64 j + 16 k, +16): hi pairs in 8 columns of the 32-column block the values came from, lo 16 further
+              const uint32_t a_hi = tmem_base + uint32_t(j * kBK + (k >> 1) * 32 + (k & 1) * 8), a_lo = a_hi + 16;
+              umma_f16_ts<kCtas>(d2, a_hi, db_hi + adv, idesc2, (first && k == 0) ? 0u : 1u);
+              umma_f16_ts<kCtas>(d2, a_hi, db_lo + adv, idesc2, 1);
+              umma_f16_ts<kCtas>(d2, a_lo, db_hi + adv, idesc2, 1);
+            } else {
+              umma_f16<kCtas>(d2, da_hi + adv, db_hi + adv, idesc2, (first && k == 0) ? 0u : 1u);
+              umma_f16<kCtas>(d2, da_hi + adv, db_lo + adv, idesc2, 1);
+              umma_f16<kCtas>(d2, da_lo + adv, db_hi + adv, idesc2, 1);
+            }
           }
           umma_commit<kCtas>(&empty[s]);
           if (j == ti.nslices - 1) umma_commit<kCtas>(acc2_full);
@@ -453,7 +492,7 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
       tc_fence_after();
       for (int j = 0; j < ti.nslices; ++j, ++it) {
         const int s = it % kStages;
-        mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);   // the MMAs that last read this stage have retired
+        if (!kA2Tmem) mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);   // the MMAs that last read this stage have retired
         FCT_MARK(1);   // epi1: waiting for the ring stage
         uint8_t* st = smem + s * kStageBytes;
         uint8_t* row_hi = st + row_l * kRowBytes;
@@ -481,25 +520,46 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[i] = make_float4(a[2 * i].x * inv, a[2 * i].y * inv, a[2 * i + 1].x * inv, a[2 * i + 1].y * inv);
           }
+          if (kA2Tmem) {
+            // back into the 32 columns just read: [c0, c0 + 16) the hi pairs, [c0 + 16, c0 + 32) the lo pairs (TS-mode A operand)
+            uint32_t hw[16], lw[16];
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {     // 16-byte chunks of 8 fp16; swizzle: chunk ^= row % 8 (128 B) | (row / 2) % 4 (64 B)
-            uint32_t hw[4], lw[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 v = a[4 * cc + e];
+            for (int e = 0; e < 16; ++e) {
+              const float2 v = a[e];
               const __half2 h = __floats2half2_rn(v.x, v.y);
               const float2 lf = sub2(v, make_float2(__low2float(h), __high2float(h)));
               const __half2 l = __floats2half2_rn(lf.x, lf.y);
               hw[e] = *reinterpret_cast<const uint32_t*>(&h);
               lw[e] = *reinterpret_cast<const uint32_t*>(&l);
             }
-            const int chunk = kBK == 64 ? ((half * 4 + cc) ^ (row_l & 7)) * 16 : (cc ^ ((row_l >> 1) & 3)) * 16;
-            *reinterpret_cast<uint4*>(row_hi + chunk) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *reinterpret_cast<uint4*>(row_hi + kABytes + chunk) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            tmem_st_x16(tmem_base + lane_addr + c0, hw);
+            tmem_st_x16(tmem_base + lane_addr + c0 + 16, lw);
+          } else {
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {     // 16-byte chunks of 8 fp16; swizzle: chunk ^= row % 8 (128 B) | (row / 2) % 4 (64 B)
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 v = a[4 * cc + e];
+                const __half2 h = __floats2half2_rn(v.x, v.y);
+                const float2 lf = sub2(v, make_float2(__low2float(h), __high2float(h)));
+                const __half2 l = __floats2half2_rn(lf.x, lf.y);
+                hw[e] = *reinterpret_cast<const uint32_t*>(&h);
+                lw[e] = *reinterpret_cast<const uint32_t*>(&l);
+              }
+              const int chunk = kBK == 64 ? ((half * 4 + cc) ^ (row_l & 7)) * 16 : (cc ^ ((row_l >> 1) & 3)) * 16;
+              *reinterpret_cast<uint4*>(row_hi + chunk) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              *reinterpret_cast<uint4*>(row_hi + kABytes + chunk) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
           }
         }
-        FCT_MARK(2);   // epi1: tcgen05.ld + math + st.shared
-        asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes -> visible to the MMA (async proxy)
+        FCT_MARK(2);   // epi1: tcgen05.ld + math + store
+        if (kA2Tmem) {
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+        } else {
+          asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes -> visible to the MMA (async proxy)
+        }
         __syncwarp();
         if (lane == 0) arrive_at_leader(&a2_full[s]);
         FCT_MARK(3);   // epi1: fence + arrive
