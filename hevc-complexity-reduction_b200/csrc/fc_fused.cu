@@ -57,7 +57,8 @@ struct Geo {
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBRowsMax * kRowBytes;     // K = 64: 96 KB | 64 KB
   static constexpr int kStages = 192 * 1024 / kStageBytes;                        // K = 64: 2 | 3
   static constexpr int kSmemBytes = kStages * kStageBytes + kTableFloats * 4 + 256 + 1024;
-  static_assert((3 * kStages + 5) * 8 <= 256, "barrier block overflows its shared-memory slot");
+  static constexpr int kA2Bars = kStages > 256 / kBK ? kStages : 256 / kBK;      // a2_full: per ring stage, or per a1 slice of a tile
+  static_assert((2 * kStages + kA2Bars + 5) * 8 <= 256, "barrier block overflows its shared-memory slot");
 };
 
 // K-major operand tile in swizzled shared memory: rows of kBK fp16 (one swizzle row), 8-row groups back to back.
@@ -261,8 +262,13 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
   uint64_t* bars = reinterpret_cast<uint64_t*>(tab + kTableFloats);
   uint64_t* full = bars;                        // [kStages]  TMA bytes landed
   uint64_t* empty = bars + kStages;             // [kStages]  MMAs that read the stage have retired
-  uint64_t* a2_full = bars + 2 * kStages;       // [kStages]  epilogue warps have written the FC2 A operand
-  uint64_t* acc1_full = bars + 3 * kStages;     // FC1 accumulator complete
+  // a2_full: the epilogue warps have written the FC2 A operand.  Through shared memory it is indexed by ring stage (the epilogue
+  // waits for the stage's `empty` first, so it can never be two phases ahead of the issuer).  Through tensor memory nothing holds
+  // the epilogue back within a tile -- with 4 slices on 3 stages it could complete the same stage's barrier TWICE before the
+  // issuer looked once (seen as a launch failure from the deadlock trap, with the QP 20~25 weights only) -- so there it is indexed
+  // by slice, one phase per tile.
+  uint64_t* a2_full = bars + 2 * kStages;       // [kA2Bars]
+  uint64_t* acc1_full = a2_full + Geo<kCtas>::kA2Bars;     // FC1 accumulator complete
   uint64_t* acc1_empty = acc1_full + 1;         // epilogue has drained accumulator 1
   uint64_t* acc2_full = acc1_full + 2;
   uint64_t* acc2_empty = acc1_full + 3;
@@ -298,7 +304,8 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a_hi), prefetch_tmap(&map_a_lo);
     prefetch_tmap(&w1_hi_t0), prefetch_tmap(&w1_lo_t0), prefetch_tmap(&w1_hi_t1), prefetch_tmap(&w1_lo_t1);
-    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 2), mbar_init(&empty[s], 1), mbar_init(&a2_full[s], kEpiWarps * kCtas);
+    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 2), mbar_init(&empty[s], 1);
+    for (int s = 0; s < Geo<kCtas>::kA2Bars; ++s) mbar_init(&a2_full[s], kEpiWarps * kCtas);
     mbar_init(acc1_full, 1), mbar_init(acc1_empty, kEpiWarps * kCtas), mbar_init(acc2_full, 1), mbar_init(acc2_empty, 4 * kCtas);
     mbar_fence_init();
   }
@@ -386,7 +393,7 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
     }
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer (the leader CTA of a pair only) -------------------------
-    int it = 0, tile_i = 0, a2_cnt[kStages] = {};
+    int it = 0, tile_i = 0, a2_cnt[Geo<kCtas>::kA2Bars] = {};
 #ifdef ETHCNN_EXP_FC_TIMING
     unsigned long long fct_acc[8] = {};
 #endif
@@ -430,8 +437,9 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
         int head, kofs, n2, acc_col, first;
         fc2_slice(ti.type, j, head, kofs, n2, acc_col, first);
         mbar_wait(&full[s], (it / kStages) & 1);
-        wait_shared(&a2_full[s], a2_cnt[s] & 1);
-        ++a2_cnt[s];
+        const int a2i = kA2Tmem ? j : s;   // a slice index is not used by every tile (type 0 has one slice less): count uses
+        wait_shared(&a2_full[a2i], a2_cnt[a2i] & 1);
+        ++a2_cnt[a2i];
         FCT_MARK(4);   // FC2: waiting for W2 and the a1 slice from the epilogue warps
         tc_fence_after();
         __syncwarp();
@@ -561,7 +569,7 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
           asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes -> visible to the MMA (async proxy)
         }
         __syncwarp();
-        if (lane == 0) arrive_at_leader(&a2_full[s]);
+        if (lane == 0) arrive_at_leader(&a2_full[kA2Tmem ? j : s]);
         FCT_MARK(3);   // epi1: fence + arrive
       }
       tc_fence_before();
