@@ -427,7 +427,15 @@ conv_features_kernel(const __grid_constant__ CUtensorMap tmap, const ConvLaunch 
   {
     const float4* src = reinterpret_cast<const float4*>(p.convw);
     float4* dst = reinterpret_cast<float4*>(wsm);
-    for (int i = threadIdx.x; i < kConvFloats / 4; i += kConvThreads) dst[i] = src[i];
+    // all of a thread's loads in flight before its first store: a rolled load -> store loop pays the L2 latency ten times in a row
+    constexpr int kCopyIters = (kConvFloats / 4 + kConvThreads - 1) / kConvThreads;
+    float4 v[kCopyIters];
+#pragma unroll
+    for (int k = 0; k < kCopyIters; ++k)
+      if (int(threadIdx.x) + k * kConvThreads < kConvFloats / 4) v[k] = src[threadIdx.x + k * kConvThreads];
+#pragma unroll
+    for (int k = 0; k < kCopyIters; ++k)
+      if (int(threadIdx.x) + k * kConvThreads < kConvFloats / 4) dst[threadIdx.x + k * kConvThreads] = v[k];
   }
 #ifdef ETHCNN_EXP_UMMA_LOAD
   __shared__ uint32_t exp_tmem_slot;

@@ -295,11 +295,28 @@ __device__ __forceinline__ void fc_fused_body(const CUtensorMap& map_a_hi, const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   pdl_launch_dependents();   // the gate kernel may be scheduled behind us; it waits for our completion itself
-  for (int i = threadIdx.x; i < kW3Floats; i += kThreads) w3s[i] = p.w3[i];
+  {
+    // Tables from global memory: every load of the thread is in flight before its first store (a rolled scalar copy loop pays
+    // the L2 latency once per iteration, ~5 us of prologue that the CTAs starting behind the last conv CTAs cannot hide).
+    constexpr int kW3Vec = kW3Floats / 4, kW3Iters = (kW3Vec + kThreads - 1) / kThreads;
+    static_assert(kW3Floats % 4 == 0 && kFc1 % 4 == 0 && kFc1 / 4 <= kThreads, "vector copy of the tables");
+    const float4* w3g = reinterpret_cast<const float4*>(p.w3);
+    float4 wv[kW3Iters];
+#pragma unroll
+    for (int k = 0; k < kW3Iters; ++k)
+      if (int(threadIdx.x) + k * kThreads < kW3Vec) wv[k] = w3g[threadIdx.x + k * kThreads];
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x < kFc1 / 4) bv = reinterpret_cast<const float4*>(p.b1)[threadIdx.x];
+#pragma unroll
+    for (int k = 0; k < kW3Iters; ++k)
+      if (int(threadIdx.x) + k * kThreads < kW3Vec) reinterpret_cast<float4*>(w3s)[threadIdx.x + k * kThreads] = wv[k];
+    // b1 pre-scaled by 2^a1_exp: leaky(acc u + b) 2^e == leaky(acc (u 2^e) + b 2^e) exactly, one multiply less per activation
+    if (threadIdx.x < kFc1 / 4)
+      reinterpret_cast<float4*>(b1s)[threadIdx.x] =
+          make_float4(bv.x * p.a1_scale, bv.y * p.a1_scale, bv.z * p.a1_scale, bv.w * p.a1_scale);
+  }
   for (int i = threadIdx.x; i < 336; i += kThreads) b2s[i] = p.b2eff[i];
   if (threadIdx.x < 21) b3s[threadIdx.x] = p.b3eff[threadIdx.x];
-  // b1 pre-scaled by 2^a1_exp: leaky(acc u + b) 2^e == leaky(acc (u 2^e) + b 2^e) exactly, one multiply less per activation
-  for (int i = threadIdx.x; i < kFc1; i += kThreads) b1s[i] = p.b1[i] * p.a1_scale;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a_hi), prefetch_tmap(&map_a_lo);
