@@ -44,8 +44,8 @@ ALG_FLOP_PER_CTU = 3104298              # 2 * 1 552 149 MAC
 CONV_FLOP_PER_CTU = 2 * 279552
 SCRATCH_BYTES_PER_CTU = 2 * 2 * 2688    # the features as fp16 hi + lo, written by the conv kernel and read by the FC kernel
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch, per CTU, from the `ncu --set full` captures under profiles/
-NCU_DRAM_BYTES_PER_CTU = {"conv": (104.615936e6 + 224.256000e6) / 25500, "fc1": (290.022144e6 + 5.810432e6) / 25500}
-NCU_DRAM_SOURCE = {"conv": "profiles/r02i_conv.md", "fc1": "profiles/r02i_fc_pair.md"}
+NCU_DRAM_BYTES_PER_CTU = {"conv": (104.592384e6 + 223.902464e6) / 25500, "fc1": (289.413376e6 + 5.936640e6) / 25500}
+NCU_DRAM_SOURCE = {"conv": "profiles/r02j_conv.md", "fc1": "profiles/r02j_fc_pair.md"}
 
 MODE_AI, MODE_LDP = 0, 1
 CONFIGS = {

@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Turn the bench.py JSON lines kept under profiles/ into profiles/<round>_summary.md.
 
-    python tools/summarize_bench.py r02 1=profiles/r02i_bench_n1.json 2=profiles/r02i_bench_n2.json ... \
-        [--reference profiles/r02i_bench_reference.json] [--cli8 profiles/r02i_cli_wallclock_8gpu_server.txt]
+    python tools/summarize_bench.py r02 1=profiles/r02j_bench_n1.json 2=profiles/r02i_bench_n2.json ... \
+        [--reference profiles/r02j_bench_reference.json] [--cli8 profiles/r02i_cli_wallclock_8gpu_server.txt]
 
 Every number in the output is read from those files; nothing is typed in by hand."""
 import argparse
@@ -35,6 +35,7 @@ def main():
     ap.add_argument("lines", nargs="+", help="N=path of a bench.py line")
     ap.add_argument("--reference")
     ap.add_argument("--cli8")
+    ap.add_argument("--note", help="a sentence appended to the introduction (e.g. which lines predate a kernel change)")
     a = ap.parse_args()
     runs = {}
     for spec in a.lines:
@@ -49,7 +50,8 @@ def main():
         ", " + os.path.basename(a.reference) if a.reference else ""))
     w("`python bench.py --steps %d --warmup %d` (N = 1) / the same under torchrun (N > 1), each on a fresh box. `value` = "
       "device-resident CTU/s (CUDA events on the launching stream, max over ranks, nothing but the library's launches in the "
-      "timed region), `e2e` = host API from pinned memory: H2D + kernels + D2H inside the timed region.\n" % (d1["steps"], d1["warmup"]))
+      "timed region), `e2e` = host API from pinned memory: H2D + kernels + D2H inside the timed region.%s\n" % (
+          d1["steps"], d1["warmup"], "  " + a.note if a.note else ""))
 
     w("## Headline: BASELINE %s, weak scaling\n" % d1["config"]["workload"])
     w("| N | value CTU/s | per GPU | vs N x (N = 1) | ms per step | e2e CTU/s | bare pinned-H2D ceiling of the box | e2e / ceiling | N-GPU == 1-GPU rows |")
